@@ -1,0 +1,697 @@
+// C-ABI of the B200-native kd-tree neighbour resampling path (see include/prs_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "prs_common.cuh"
+#include "prs_index.cuh"
+#include "prs_proj.cuh"
+#include "prs_query.cuh"
+#include "prs_scan.cuh"
+
+using namespace prs;
+
+namespace {
+
+constexpr int TPB = 256;
+inline unsigned blocks_for(int64_t n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
+
+// ------------------------------------------------------------------------------------------ small kernels
+template <typename T>
+__global__ void lonlat_to_xyz_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, T *__restrict__ xyz)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T x, y, z;
+    lonlat_to_xyz(lon[i], lat[i], x, y, z);
+    xyz[3 * i] = x;
+    xyz[3 * i + 1] = y;
+    xyz[3 * i + 2] = z;
+}
+
+template <typename T>
+__global__ void area_lonlats_kernel(const prs_proj_params P, const prs_area_grid g, int64_t row0, int64_t row_step,
+                                    int64_t nrows, int64_t col0, int64_t col_step, int64_t ncols, T *lon_out, T *lat_out,
+                                    T *xyz_out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows * ncols) return;
+    int64_t r = i / ncols, c = i - r * ncols;
+    T lon, lat;
+    area_pixel_lonlat<T>(P, g, row0 + r * row_step, col0 + c * col_step, lon, lat);
+    if (lon_out) lon_out[i] = lon;
+    if (lat_out) lat_out[i] = lat;
+    if (xyz_out) {
+        T x, y, z;
+        lonlat_to_xyz(lon, lat, x, y, z);
+        xyz_out[3 * i] = x;
+        xyz_out[3 * i + 1] = y;
+        xyz_out[3 * i + 2] = z;
+    }
+}
+
+template <typename T>
+__global__ void valid_mask_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, const prs_reduce_box box,
+                                  const uint8_t *__restrict__ premask, uint8_t *__restrict__ valid)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T lo = lon[i], la = lat[i];
+    bool ok = lonlat_in_range<T>(lo, la);
+    if (premask && premask[i]) ok = false;
+    // data_reduce.py:282-305; numpy promotes the float32 coordinates to float64 against the float64 bounds
+    double dlo = (double)lo, dla = (double)la;
+    switch (box.kind) {
+    case PRS_REDUCE_LAT_GE:
+        ok = ok && (dla >= box.lat_min);
+        break;
+    case PRS_REDUCE_LAT_LE:
+        ok = ok && (dla <= box.lat_max);
+        break;
+    case PRS_REDUCE_BOX:
+        ok = ok && (dla >= box.lat_min) && (dla <= box.lat_max) && (dlo >= box.lon_min) && (dlo <= box.lon_max);
+        break;
+    case PRS_REDUCE_BOX_DATELINE:
+        ok = ok && (dla >= box.lat_min) && (dla <= box.lat_max) &&
+             (((dlo >= box.lon_min) && (dlo <= 180.0)) || ((dlo <= box.lon_max) && (dlo >= -180.0)));
+        break;
+    default:
+        break;
+    }
+    valid[i] = ok ? 1 : 0;
+}
+
+__global__ void gather_nearest_kernel(const uint32_t *__restrict__ index, int64_t n_out, uint32_t n_valid,
+                                      const uint32_t *__restrict__ rank_to_source, const void *data, int64_t row_bytes,
+                                      int vec, const void *fill_row, void *out)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_out) return;
+    uint32_t r = index[p];
+    const void *src;
+    if (r >= n_valid) {
+        src = fill_row;
+    } else {
+        uint32_t s = rank_to_source ? __ldg(rank_to_source + r) : r;
+        src = (const char *)data + (size_t)s * row_bytes;
+    }
+    copy_row((char *)out + (size_t)p * row_bytes, src, row_bytes, vec);
+}
+
+struct WeightedParams {
+    const uint32_t *index;
+    const void *dist;
+    int64_t n_out;
+    int k;
+    uint32_t n_valid;
+    const uint32_t *rank_to_source;
+    const void *data;
+    int channels;
+    const void *weights;  // [n_planes][n_out*k] or NULL
+    const int32_t *plane_of_channel;  // device
+    const double *sigma2;             // device or NULL
+    double fill;
+    void *out, *stddev_out, *count_out;
+    uint32_t first_valid_source;
+};
+
+// get_sample_from_neighbour_info('custom') on precomputed neighbour info, runtime k (kd_tree.py:741-859).
+// Tw: dtype of distances / explicit weights; Td: data dtype; Ta: accumulation and output dtype.
+template <typename Tw, typename Td, typename Ta> __global__ void gather_weighted_kernel(const WeightedParams P)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_out) return;
+    const int k = P.k, C = P.channels;
+    const uint32_t *idx = P.index + (size_t)p * k;
+    const bool want_uncert = P.stddev_out != nullptr;
+    for (int c = 0; c < C; ++c) {
+        const Tw *wplane = P.weights ? (const Tw *)P.weights + ((size_t)P.plane_of_channel[c] * P.n_out + p) * k : nullptr;
+        Ta res = 0, norm = 0;
+        for (int i = 0; i < k; ++i) {
+            uint32_t r = idx[i];
+            bool missing = r >= P.n_valid;
+            uint32_t s = missing ? P.first_valid_source : (P.rank_to_source ? __ldg(P.rank_to_source + r) : r);
+            Ta v = (Ta)__ldg((const Td *)P.data + (size_t)s * C + c);
+            Ta w;
+            if (wplane) {
+                w = (Ta)wplane[i];
+            } else {
+                Tw d = missing ? (Tw)1 : ((const Tw *)P.dist)[(size_t)p * k + i];
+                w = (Ta)Ar<Tw>::exp(Ar<Tw>::div(-Ar<Tw>::mul(d, d), (Tw)P.sigma2[c]));
+            }
+            Ta wt = missing ? Ar<Ta>::mul((Ta)0, w) : w;
+            res = Ar<Ta>::add(res, Ar<Ta>::mul(wt, v));
+            norm = Ar<Ta>::add(norm, wt);
+        }
+        if (norm > 0)
+            res = Ar<Ta>::div(res, norm);
+        else
+            res = (Ta)P.fill;
+        ((Ta *)P.out)[(size_t)p * C + c] = res;
+        if (want_uncert) {
+            int count = 0;
+            Ta norm_sqr = 0, sd = 0;
+            for (int i = 0; i < k; ++i) {
+                uint32_t r = idx[i];
+                bool missing = r >= P.n_valid;
+                uint32_t s = missing ? P.first_valid_source : (P.rank_to_source ? __ldg(P.rank_to_source + r) : r);
+                Ta v = (Ta)__ldg((const Td *)P.data + (size_t)s * C + c);
+                Ta w;
+                if (wplane) {
+                    w = (Ta)wplane[i];
+                } else {
+                    Tw d = missing ? (Tw)1 : ((const Tw *)P.dist)[(size_t)p * k + i];
+                    w = (Ta)Ar<Tw>::exp(Ar<Tw>::div(-Ar<Tw>::mul(d, d), (Tw)P.sigma2[c]));
+                }
+                Ta wt = missing ? Ar<Ta>::mul((Ta)0, w) : w;
+                count += missing ? 0 : 1;
+                norm_sqr = Ar<Ta>::add(norm_sqr, Ar<Ta>::mul(wt, wt));
+                Ta val = missing ? Ar<Ta>::mul((Ta)0, v) : v;
+                Ta dv = Ar<Ta>::sub(val, res);
+                sd = Ar<Ta>::add(sd, Ar<Ta>::mul(wt, Ar<Ta>::mul(dv, dv)));
+            }
+            Ta sdv = count > 1
+                         ? Ar<Ta>::sqrt(Ar<Ta>::mul(Ar<Ta>::div(norm, Ar<Ta>::sub(Ar<Ta>::mul(norm, norm), norm_sqr)), sd))
+                         : Ar<Ta>::nan();
+            ((Ta *)P.stddev_out)[(size_t)p * C + c] = sdv;
+            ((Ta *)P.count_out)[(size_t)p * C + c] = (Ta)count;
+        }
+    }
+}
+
+__global__ void compact_rows_kernel(const uint8_t *__restrict__ mask, const uint32_t *__restrict__ pos, int64_t n,
+                                    int64_t row_bytes, int vec, const void *in, void *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !mask[i]) return;
+    copy_row((char *)out + (size_t)pos[i] * row_bytes, (const char *)in + (size_t)i * row_bytes, row_bytes, vec);
+}
+
+__global__ void scatter_rows_kernel(const uint8_t *__restrict__ mask, const uint32_t *__restrict__ pos, int64_t n,
+                                    int64_t row_bytes, int vec, const void *in, const void *fill_row, void *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const void *src = mask[i] ? (const void *)((const char *)in + (size_t)pos[i] * row_bytes) : fill_row;
+    copy_row((char *)out + (size_t)i * row_bytes, src, row_bytes, vec);
+}
+
+__global__ void rank_to_source_kernel(const uint8_t *__restrict__ valid, const uint32_t *__restrict__ pos, int64_t n,
+                                      uint32_t *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !valid[i]) return;
+    out[pos[i]] = (uint32_t)i;
+}
+
+int pick_vec(int64_t row_bytes, const void *a, const void *b, const void *c)
+{
+    uintptr_t bits = (uintptr_t)row_bytes | (uintptr_t)a | (uintptr_t)b | (uintptr_t)c;
+    if ((bits & 15) == 0) return 16;
+    if ((bits & 7) == 0) return 8;
+    if ((bits & 3) == 0) return 4;
+    if ((bits & 1) == 0) return 2;
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------ query launch
+struct TargetTables {
+    void *col_tab = nullptr, *row_tab = nullptr;
+    uint8_t *col_ok = nullptr, *row_ok = nullptr;
+};
+
+template <typename T, int K> int launch_query_tk(const QueryParams &P, const IndexView<T> &ix, int tk, cudaStream_t st)
+{
+    unsigned grid = blocks_for(P.n_t);
+    if (grid == 0) return PRS_OK;
+    switch (tk) {
+    case PRS_TK_LONLAT:
+        query_kernel<T, K, PRS_TK_LONLAT><<<grid, TPB, 0, st>>>(P, ix);
+        break;
+    case PRS_TK_AREA_SEP:
+        query_kernel<T, K, PRS_TK_AREA_SEP><<<grid, TPB, 0, st>>>(P, ix);
+        break;
+    default:
+        query_kernel<T, K, PRS_TK_AREA_GEN><<<grid, TPB, 0, st>>>(P, ix);
+        break;
+    }
+    PRS_CKL();
+    return PRS_OK;
+}
+
+template <typename T> int launch_query_t(QueryParams &P, const prs_index *index, const prs_target *tg, cudaStream_t st)
+{
+    IndexView<T> ix;
+    ix.recs = index->n_indexed > 0 ? (const Rec<T> *)index->recs : nullptr;
+    ix.cell_start = index->cell_start;
+    ix.coarse_start = index->coarse_start;
+    ix.rank = index->rank;
+    ix.G = index->G;
+    ix.Gc = index->Gc;
+    ix.n_valid = (uint32_t)index->n_valid;
+    ix.first_valid_source = index->first_valid_source;
+    int tk = PRS_TK_LONLAT;
+    TargetTables tabs;
+    P.n_t = tg->n;
+    P.valid_extra = tg->valid_extra;
+    if (tg->kind == PRS_TARGET_AREA) {
+        if (tg->n != tg->nrows * tg->grid.width) return fail(PRS_EINVAL, "target.n != nrows * width");
+        P.proj = tg->proj;
+        P.grid = tg->grid;
+        P.row0 = tg->row0;
+        bool separable = tg->proj.kind == PRS_PROJ_LONGLAT || tg->proj.kind == PRS_PROJ_EQC || tg->proj.kind == PRS_PROJ_MERC;
+        if (separable && tg->n > 0) {
+            tk = PRS_TK_AREA_SEP;
+            int64_t W = tg->grid.width, H = tg->nrows;
+            PRS_CK(cudaMallocAsync(&tabs.col_tab, sizeof(ColTab<T>) * (size_t)W, st));
+            PRS_CK(cudaMallocAsync(&tabs.row_tab, sizeof(RowTab<T>) * (size_t)H, st));
+            PRS_CK(cudaMallocAsync((void **)&tabs.col_ok, (size_t)W, st));
+            PRS_CK(cudaMallocAsync((void **)&tabs.row_ok, (size_t)H, st));
+            area_tables_kernel<T><<<blocks_for(W + H), TPB, 0, st>>>(tg->proj, tg->grid, tg->row0, H, (ColTab<T> *)tabs.col_tab,
+                                                                      tabs.col_ok, (RowTab<T> *)tabs.row_tab, tabs.row_ok);
+            PRS_CKL();
+            P.col_tab = tabs.col_tab;
+            P.row_tab = tabs.row_tab;
+            P.col_ok = tabs.col_ok;
+            P.row_ok = tabs.row_ok;
+        } else {
+            tk = PRS_TK_AREA_GEN;
+        }
+    } else {
+        P.tlon = tg->lon;
+        P.tlat = tg->lat;
+    }
+    int rc;
+    int k = P.k;
+    if (k <= 1)
+        rc = launch_query_tk<T, 1>(P, ix, tk, st);
+    else if (k <= 4)
+        rc = launch_query_tk<T, 4>(P, ix, tk, st);
+    else if (k <= 8)
+        rc = launch_query_tk<T, 8>(P, ix, tk, st);
+    else if (k <= 16)
+        rc = launch_query_tk<T, 16>(P, ix, tk, st);
+    else if (k <= 32)
+        rc = launch_query_tk<T, 32>(P, ix, tk, st);
+    else
+        return fail(PRS_ENOSUP, "neighbours > 32 is not supported");
+    if (tabs.col_tab) {
+        PRS_CK(cudaFreeAsync(tabs.col_tab, st));
+        PRS_CK(cudaFreeAsync(tabs.row_tab, st));
+        PRS_CK(cudaFreeAsync(tabs.col_ok, st));
+        PRS_CK(cudaFreeAsync(tabs.row_ok, st));
+    }
+    return rc;
+}
+
+int launch_query(QueryParams &P, const prs_index *index, const prs_target *tg, cudaStream_t st)
+{
+    if (!index || !tg) return fail(PRS_EINVAL, "null index/target");
+    if (tg->dtype != index->tree_dtype && tg->kind == PRS_TARGET_LONLAT)
+        return fail(PRS_EINVAL, "target lon/lat dtype must equal the tree dtype (kd_tree.py:536-542)");
+    if (P.k < 1) return fail(PRS_EINVAL, "neighbours must be >= 1");
+    if (index->tree_dtype == PRS_F32) return launch_query_t<float>(P, index, tg, st);
+    return launch_query_t<double>(P, index, tg, st);
+}
+
+int read_flags(unsigned int *flags_dev, int64_t *flags_host, cudaStream_t st)
+{
+    unsigned int h[2] = {0, 0};
+    PRS_CK(cudaMemcpyAsync(h, flags_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
+    PRS_CK(cudaStreamSynchronize(st));
+    PRS_CK(cudaFreeAsync(flags_dev, st));
+    flags_host[0] = h[0];
+    flags_host[1] = h[1];
+    return PRS_OK;
+}
+
+}  // namespace
+
+// ============================================================================================== C-ABI
+extern "C" {
+
+int prs_abi_version(void) { return PRS_ABI_VERSION; }
+const char *prs_last_error(void) { return err_slot().c_str(); }
+
+int prs_lonlat_to_xyz(const void *lon, const void *lat, int64_t n, int dtype, void *xyz_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return PRS_OK;
+    if (dtype == PRS_F32)
+        lonlat_to_xyz_kernel<float><<<blocks_for(n), TPB, 0, st>>>((const float *)lon, (const float *)lat, n, (float *)xyz_out);
+    else if (dtype == PRS_F64)
+        lonlat_to_xyz_kernel<double><<<blocks_for(n), TPB, 0, st>>>((const double *)lon, (const double *)lat, n, (double *)xyz_out);
+    else
+        return fail(PRS_EINVAL, "dtype must be PRS_F32 or PRS_F64");
+    PRS_CKL();
+    return PRS_OK;
+}
+
+int prs_area_lonlats(const prs_proj_params *proj, const prs_area_grid *grid, int dtype, int64_t row0, int64_t row_step,
+                     int64_t nrows, int64_t col0, int64_t col_step, int64_t ncols, void *lon_out, void *lat_out,
+                     void *xyz_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!proj || !grid) return fail(PRS_EINVAL, "null proj/grid");
+    int64_t n = nrows * ncols;
+    if (n <= 0) return PRS_OK;
+    if (dtype == PRS_F32)
+        area_lonlats_kernel<float><<<blocks_for(n), TPB, 0, st>>>(*proj, *grid, row0, row_step, nrows, col0, col_step, ncols,
+                                                                   (float *)lon_out, (float *)lat_out, (float *)xyz_out);
+    else if (dtype == PRS_F64)
+        area_lonlats_kernel<double><<<blocks_for(n), TPB, 0, st>>>(*proj, *grid, row0, row_step, nrows, col0, col_step, ncols,
+                                                                    (double *)lon_out, (double *)lat_out, (double *)xyz_out);
+    else
+        return fail(PRS_EINVAL, "dtype must be PRS_F32 or PRS_F64");
+    PRS_CKL();
+    return PRS_OK;
+}
+
+int prs_valid_mask(const void *lon, const void *lat, int64_t n, int dtype, const prs_reduce_box *box, const uint8_t *premask,
+                   uint8_t *valid_out, int64_t *n_valid_host, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    prs_reduce_box b;
+    memset(&b, 0, sizeof(b));
+    if (box) b = *box;
+    if (n > 0) {
+        if (dtype == PRS_F32)
+            valid_mask_kernel<float><<<blocks_for(n), TPB, 0, st>>>((const float *)lon, (const float *)lat, n, b, premask, valid_out);
+        else if (dtype == PRS_F64)
+            valid_mask_kernel<double><<<blocks_for(n), TPB, 0, st>>>((const double *)lon, (const double *)lat, n, b, premask, valid_out);
+        else
+            return fail(PRS_EINVAL, "dtype must be PRS_F32 or PRS_F64");
+        PRS_CKL();
+    }
+    if (n_valid_host) {
+        *n_valid_host = 0;
+        if (n > 0) {
+            uint32_t *tmp = nullptr, *tot = nullptr;
+            PRS_CK(cudaMallocAsync((void **)&tmp, sizeof(uint32_t) * (size_t)n, st));
+            PRS_CK(cudaMallocAsync((void **)&tot, sizeof(uint32_t), st));
+            int rc = scan_u32<uint8_t>(valid_out, tmp, n, 0, tot, st);
+            if (rc != PRS_OK) return rc;
+            uint32_t h = 0;
+            PRS_CK(cudaMemcpyAsync(&h, tot, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            PRS_CK(cudaStreamSynchronize(st));
+            PRS_CK(cudaFreeAsync(tmp, st));
+            PRS_CK(cudaFreeAsync(tot, st));
+            *n_valid_host = h;
+        }
+    }
+    return PRS_OK;
+}
+
+int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, const uint8_t *valid, const uint8_t *exclude,
+                    int tree_dtype, int k_hint, double radius_hint, prs_index **index_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!index_out) return fail(PRS_EINVAL, "index_out is null");
+    if (n <= 0 || n >= 0xFFFFFFFFLL) return fail(PRS_EINVAL, "source size must be in [1, 2^32 - 2]");
+    if (dtype != tree_dtype)
+        return fail(PRS_ENOSUP, "lon/lat dtype must equal tree dtype (cast on the host side of the ABI)");
+    if (!valid) return fail(PRS_EINVAL, "valid mask is required (prs_valid_mask)");
+    prs_index *ix = new prs_index();
+    memset(ix, 0, sizeof(*ix));
+    ix->tree_dtype = tree_dtype;
+    ix->n_source = n;
+    int rc;
+    if (tree_dtype == PRS_F32)
+        rc = index_build_t<float>((const float *)lon, (const float *)lat, n, valid, exclude, k_hint, radius_hint, ix, st);
+    else if (tree_dtype == PRS_F64)
+        rc = index_build_t<double>((const double *)lon, (const double *)lat, n, valid, exclude, k_hint, radius_hint, ix, st);
+    else
+        rc = fail(PRS_EINVAL, "tree_dtype must be PRS_F32 or PRS_F64");
+    if (rc != PRS_OK) {
+        prs_index_destroy(ix);
+        return rc;
+    }
+    *index_out = ix;
+    return PRS_OK;
+}
+
+int prs_index_destroy(prs_index *ix)
+{
+    if (!ix) return PRS_OK;
+    if (ix->recs) cudaFree(ix->recs);
+    if (ix->cell_start) cudaFree(ix->cell_start);
+    if (ix->coarse_start) cudaFree(ix->coarse_start);
+    if (ix->rank) cudaFree(ix->rank);
+    delete ix;
+    return PRS_OK;
+}
+
+int prs_index_info(const prs_index *ix, int64_t info[8])
+{
+    if (!ix || !info) return fail(PRS_EINVAL, "null argument");
+    info[0] = ix->n_source;
+    info[1] = ix->n_valid;
+    info[2] = ix->n_indexed;
+    info[3] = ix->G;
+    info[4] = (int64_t)ix->bytes;
+    info[5] = ix->tree_dtype;
+    info[6] = ix->Gc;
+    info[7] = ix->all_valid;
+    return PRS_OK;
+}
+
+int prs_query(const prs_index *index, const prs_target *target, int k, double radius, uint32_t *idx_out, void *dist_out,
+              uint8_t *valid_out, int64_t *flags_host, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    QueryParams P;
+    memset(&P, 0, sizeof(P));
+    P.radius = radius;
+    P.k = k;
+    P.mode = PRS_EPI_INFO;
+    P.idx_out = idx_out;
+    P.dist_out = dist_out;
+    P.valid_out = valid_out;
+    if (!idx_out) return fail(PRS_EINVAL, "idx_out is null");
+    if (flags_host) {
+        PRS_CK(cudaMallocAsync((void **)&P.flags, 2 * sizeof(unsigned int), st));
+        PRS_CK(cudaMemsetAsync(P.flags, 0, 2 * sizeof(unsigned int), st));
+    }
+    int rc = launch_query(P, index, target, st);
+    if (rc != PRS_OK) return rc;
+    if (flags_host) return read_flags(P.flags, flags_host, st);
+    return PRS_OK;
+}
+
+int prs_resample_nearest(const prs_index *index, const prs_target *target, double radius, const void *data,
+                         int64_t row_bytes, const void *fill_row, void *out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!data || !fill_row || !out || row_bytes <= 0) return fail(PRS_EINVAL, "bad data/fill/out");
+    QueryParams P;
+    memset(&P, 0, sizeof(P));
+    P.radius = radius;
+    P.k = 1;
+    P.mode = PRS_EPI_NEAREST;
+    P.data = data;
+    P.fill_row = fill_row;
+    P.out = out;
+    P.row_bytes = row_bytes;
+    P.vec = pick_vec(row_bytes, data, fill_row, out);
+    return launch_query(P, index, target, st);
+}
+
+int prs_resample_gauss(const prs_index *index, const prs_target *target, int k, double radius, const void *data,
+                       int data_dtype, int channels, const double *sigmas_host, double fill, void *out, void *stddev_out,
+                       void *count_out, int64_t *flags_host, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!index || !data || !out || channels < 1 || !sigmas_host) return fail(PRS_EINVAL, "bad argument");
+    if ((stddev_out == nullptr) != (count_out == nullptr)) return fail(PRS_EINVAL, "stddev_out and count_out go together");
+    QueryParams P;
+    memset(&P, 0, sizeof(P));
+    P.radius = radius;
+    P.k = k;
+    P.mode = PRS_EPI_GAUSS;
+    P.data = data;
+    P.out = out;
+    P.channels = channels;
+    P.data_f64 = data_dtype == PRS_F64;
+    // numpy promotion in _resample_with_weights: multi-channel weights are float64 (np.ones(n) * w, kd_tree.py:783)
+    P.acc_f64 = (channels > 1) || P.data_f64 || index->tree_dtype == PRS_F64;
+    P.fill = fill;
+    P.stddev_out = stddev_out;
+    P.count_out = count_out;
+    std::vector<double> s2(channels);
+    bool uniform = true;
+    for (int c = 0; c < channels; ++c) {
+        s2[c] = sigmas_host[c] * sigmas_host[c];
+        if (s2[c] != s2[0]) uniform = false;
+    }
+    P.uniform_sigma = uniform;
+    double *s2_dev = nullptr;
+    PRS_CK(cudaMallocAsync((void **)&s2_dev, sizeof(double) * channels, st));
+    PRS_CK(cudaMemcpyAsync(s2_dev, s2.data(), sizeof(double) * channels, cudaMemcpyHostToDevice, st));
+    PRS_CK(cudaStreamSynchronize(st));  // s2 is a stack-owned staging buffer
+    P.sigma2 = s2_dev;
+    if (flags_host) {
+        PRS_CK(cudaMallocAsync((void **)&P.flags, 2 * sizeof(unsigned int), st));
+        PRS_CK(cudaMemsetAsync(P.flags, 0, 2 * sizeof(unsigned int), st));
+    }
+    int rc = launch_query(P, index, target, st);
+    PRS_CK(cudaFreeAsync(s2_dev, st));
+    if (rc != PRS_OK) return rc;
+    if (flags_host) return read_flags(P.flags, flags_host, st);
+    return PRS_OK;
+}
+
+int prs_gather_nearest(const uint32_t *index, int64_t n_out, uint32_t n_valid, const uint32_t *rank_to_source,
+                       const void *data, int64_t row_bytes, const void *fill_row, void *out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_out <= 0) return PRS_OK;
+    if (!index || !data || !fill_row || !out || row_bytes <= 0) return fail(PRS_EINVAL, "bad argument");
+    int vec = pick_vec(row_bytes, data, fill_row, out);
+    gather_nearest_kernel<<<blocks_for(n_out), TPB, 0, st>>>(index, n_out, n_valid, rank_to_source, data, row_bytes, vec,
+                                                            fill_row, out);
+    PRS_CKL();
+    return PRS_OK;
+}
+
+int prs_gather_weighted(const uint32_t *index, const void *dist, int64_t n_out, int k, uint32_t n_valid,
+                        const uint32_t *rank_to_source, const void *data, int data_dtype, int channels, const void *weights,
+                        int weight_dtype, int n_planes, const int32_t *plane_of_channel_host, const double *sigmas_host,
+                        double fill, void *out, void *stddev_out, void *count_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_out <= 0) return PRS_OK;
+    if (!index || !data || !out || channels < 1 || k < 1) return fail(PRS_EINVAL, "bad argument");
+    if (!weights && !(sigmas_host && dist)) return fail(PRS_EINVAL, "need explicit weights or (dist, sigmas)");
+    if ((stddev_out == nullptr) != (count_out == nullptr)) return fail(PRS_EINVAL, "stddev_out and count_out go together");
+    WeightedParams P;
+    memset(&P, 0, sizeof(P));
+    P.index = index;
+    P.dist = dist;
+    P.n_out = n_out;
+    P.k = k;
+    P.n_valid = n_valid;
+    P.rank_to_source = rank_to_source;
+    P.data = data;
+    P.channels = channels;
+    P.weights = weights;
+    P.fill = fill;
+    P.out = out;
+    P.stddev_out = stddev_out;
+    P.count_out = count_out;
+    // first valid source row (new_data[0]) for missing neighbours
+    uint32_t fvs = 0;
+    if (rank_to_source) {
+        PRS_CK(cudaMemcpyAsync(&fvs, rank_to_source, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PRS_CK(cudaStreamSynchronize(st));
+    }
+    P.first_valid_source = fvs;
+    int32_t *planes_dev = nullptr;
+    double *s2_dev = nullptr;
+    std::vector<int32_t> planes(channels, 0);
+    std::vector<double> s2(channels, 1.0);
+    if (weights) {
+        for (int c = 0; c < channels; ++c) {
+            planes[c] = plane_of_channel_host ? plane_of_channel_host[c] : 0;
+            if (planes[c] < 0 || planes[c] >= n_planes) return fail(PRS_EINVAL, "plane_of_channel out of range");
+        }
+        PRS_CK(cudaMallocAsync((void **)&planes_dev, sizeof(int32_t) * channels, st));
+        PRS_CK(cudaMemcpyAsync(planes_dev, planes.data(), sizeof(int32_t) * channels, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int c = 0; c < channels; ++c) s2[c] = sigmas_host[c] * sigmas_host[c];
+        PRS_CK(cudaMallocAsync((void **)&s2_dev, sizeof(double) * channels, st));
+        PRS_CK(cudaMemcpyAsync(s2_dev, s2.data(), sizeof(double) * channels, cudaMemcpyHostToDevice, st));
+    }
+    PRS_CK(cudaStreamSynchronize(st));
+    P.plane_of_channel = planes_dev;
+    P.sigma2 = s2_dev;
+    bool w64 = weight_dtype == PRS_F64, d64 = data_dtype == PRS_F64;
+    bool acc64 = channels > 1 || w64 || d64;
+    unsigned grid = blocks_for(n_out);
+    if (!acc64)
+        gather_weighted_kernel<float, float, float><<<grid, TPB, 0, st>>>(P);
+    else if (w64 && d64)
+        gather_weighted_kernel<double, double, double><<<grid, TPB, 0, st>>>(P);
+    else if (w64)
+        gather_weighted_kernel<double, float, double><<<grid, TPB, 0, st>>>(P);
+    else if (d64)
+        gather_weighted_kernel<float, double, double><<<grid, TPB, 0, st>>>(P);
+    else
+        gather_weighted_kernel<float, float, double><<<grid, TPB, 0, st>>>(P);
+    PRS_CKL();
+    if (planes_dev) PRS_CK(cudaFreeAsync(planes_dev, st));
+    if (s2_dev) PRS_CK(cudaFreeAsync(s2_dev, st));
+    return PRS_OK;
+}
+
+int prs_compact_rows(const uint8_t *mask, int64_t n, int64_t row_bytes, const void *in, void *out, int64_t *n_kept_host,
+                     void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_kept_host) *n_kept_host = 0;
+    if (n <= 0) return PRS_OK;
+    uint32_t *pos = nullptr, *tot = nullptr;
+    PRS_CK(cudaMallocAsync((void **)&pos, sizeof(uint32_t) * (size_t)n, st));
+    PRS_CK(cudaMallocAsync((void **)&tot, sizeof(uint32_t), st));
+    int rc = scan_u32<uint8_t>(mask, pos, n, 0, tot, st);
+    if (rc != PRS_OK) return rc;
+    if (in && out) {
+        int vec = pick_vec(row_bytes, in, out, nullptr);
+        compact_rows_kernel<<<blocks_for(n), TPB, 0, st>>>(mask, pos, n, row_bytes, vec, in, out);
+        PRS_CKL();
+    }
+    if (n_kept_host) {
+        uint32_t h = 0;
+        PRS_CK(cudaMemcpyAsync(&h, tot, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PRS_CK(cudaStreamSynchronize(st));
+        *n_kept_host = h;
+    }
+    PRS_CK(cudaFreeAsync(pos, st));
+    PRS_CK(cudaFreeAsync(tot, st));
+    return PRS_OK;
+}
+
+int prs_rank_to_source(const uint8_t *valid, int64_t n, uint32_t *out, int64_t *n_valid_host, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_valid_host) *n_valid_host = 0;
+    if (n <= 0) return PRS_OK;
+    uint32_t *pos = nullptr, *tot = nullptr;
+    PRS_CK(cudaMallocAsync((void **)&pos, sizeof(uint32_t) * (size_t)n, st));
+    PRS_CK(cudaMallocAsync((void **)&tot, sizeof(uint32_t), st));
+    int rc = scan_u32<uint8_t>(valid, pos, n, 0, tot, st);
+    if (rc != PRS_OK) return rc;
+    if (out) {
+        rank_to_source_kernel<<<blocks_for(n), TPB, 0, st>>>(valid, pos, n, out);
+        PRS_CKL();
+    }
+    if (n_valid_host) {
+        uint32_t h = 0;
+        PRS_CK(cudaMemcpyAsync(&h, tot, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PRS_CK(cudaStreamSynchronize(st));
+        *n_valid_host = h;
+    }
+    PRS_CK(cudaFreeAsync(pos, st));
+    PRS_CK(cudaFreeAsync(tot, st));
+    return PRS_OK;
+}
+
+int prs_scatter_rows(const uint8_t *mask, int64_t n, int64_t row_bytes, const void *in, const void *fill_row, void *out,
+                     void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return PRS_OK;
+    if (!mask || !in || !fill_row || !out || row_bytes <= 0) return fail(PRS_EINVAL, "bad argument");
+    uint32_t *pos = nullptr;
+    PRS_CK(cudaMallocAsync((void **)&pos, sizeof(uint32_t) * (size_t)n, st));
+    int rc = scan_u32<uint8_t>(mask, pos, n, 0, nullptr, st);
+    if (rc != PRS_OK) return rc;
+    int vec = pick_vec(row_bytes, in, out, fill_row);
+    scatter_rows_kernel<<<blocks_for(n), TPB, 0, st>>>(mask, pos, n, row_bytes, vec, in, fill_row, out);
+    PRS_CKL();
+    PRS_CK(cudaFreeAsync(pos, st));
+    return PRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// Device-wide prefix sums (reduce-then-scan, three launches per level) used for
+//   * rank of every valid source point      (numpy boolean compaction x[valid], kd_tree.py:469-470)
+//   * cell start offsets of the counting sort (index build)
+//   * row compaction / scatter by valid_output_index (kd_tree.py:530-531, 719-723)
+#pragma once
+#include "prs_common.cuh"
+
+namespace prs {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename In> __device__ __forceinline__ uint32_t scan_load(const In *in, int64_t i, int64_t n)
+{
+    return i < n ? (uint32_t)(in[i] != 0 ? (sizeof(In) == 1 ? 1u : (uint32_t)in[i]) : 0u) : 0u;
+}
+
+template <typename In> __global__ void scan_tile_sums(const In *__restrict__ in, int64_t n, uint32_t *__restrict__ sums)
+{
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) s += scan_load(in, base + j, n);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) t += warp_sums[w];
+        sums[blockIdx.x] = t;
+    }
+}
+
+// out[i] = offset[tile] + exclusive (or inclusive) prefix within the tile.  in may alias out (uint32 in place).
+template <typename In>
+__global__ void scan_tile_apply(const In *in, int64_t n, const uint32_t *__restrict__ tile_offsets, uint32_t *out,
+                                int inclusive)
+{
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        v[j] = scan_load(in, base + j, n);
+        s += v[j];
+    }
+    uint32_t incl = s;
+    int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_sums[w];
+    uint32_t run = tile_offsets[blockIdx.x] + woff + (incl - s);
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        if (base + j < n) out[base + j] = inclusive ? run + v[j] : run;
+        run += v[j];
+    }
+}
+
+// Exclusive/inclusive scan of n items into out (uint32).  total_dev (optional) receives the grand total.
+// Temporary storage comes from the stream-ordered allocator.
+template <typename In>
+int scan_u32(const In *in, uint32_t *out, int64_t n, int inclusive, uint32_t *total_dev, cudaStream_t st)
+{
+    if (n <= 0) {
+        if (total_dev) PRS_CK(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), st));
+        return PRS_OK;
+    }
+    int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t *sums = nullptr;
+    PRS_CK(cudaMallocAsync((void **)&sums, sizeof(uint32_t) * (size_t)(tiles + 1), st));
+    scan_tile_sums<In><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, sums);
+    PRS_CKL();
+    // exclusive scan of the tile sums (recursive); sums[tiles] gets the total
+    uint32_t *tot = sums + tiles;
+    if (tiles == 1) {
+        PRS_CK(cudaMemcpyAsync(tot, sums, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        PRS_CK(cudaMemsetAsync(sums, 0, sizeof(uint32_t), st));
+    } else {
+        int rc = scan_u32<uint32_t>(sums, sums, tiles, 0, tot, st);
+        if (rc != PRS_OK) return rc;
+    }
+    scan_tile_apply<In><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, sums, out, inclusive);
+    PRS_CKL();
+    if (total_dev) PRS_CK(cudaMemcpyAsync(total_dev, tot, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    PRS_CK(cudaFreeAsync(sums, st));
+    return PRS_OK;
+}
+
+}  // namespace prs

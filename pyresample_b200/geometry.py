@@ -1,0 +1,278 @@
+"""Geometry definitions consumed by the B200 kd-tree resampling path.
+
+These are the *host-side mirror* of the parts of ``pyresample.geometry`` that the
+hot path reads (SURVEY 8b "duck-type surface"): ``size``, ``shape``, ``ndim``,
+``dtype``, ``get_lonlats(data_slice=, dtype=)``, ``get_boundary_lonlats()``,
+``get_cartesian_coords()`` plus, for areas, the projection / extent / pixel-size
+attributes of ``AreaDefinition.__init__`` (pyresample/geometry.py:1577-1619).
+They are not a re-implementation of pyresample's geometry algebra.  Genuine
+pyresample geometry objects are accepted too - :func:`as_geo_def` adapts them by
+attribute, using ``crs.to_dict()`` for the projection.
+
+Coordinate generation for areas runs on the GPU (``prs_area_lonlats`` /
+``prs_area_xyz``): there is no CPU implementation in this package.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .proj import ProjSpec, proj_to_dict
+
+
+def _np_dtype(dtype):
+    """numpy dtype of a numpy or torch dtype object."""
+    text = str(dtype)
+    if text.startswith("torch."):
+        return np.dtype(text[len("torch."):])
+    return np.dtype(dtype)
+
+
+class DimensionError(ValueError):
+    """Wrong dimensionality (pyresample/geometry.py:75)."""
+
+
+class SimpleBoundary(object):
+    """Container for the four sides of a geometry (pyresample/boundary/legacy_boundary.py:135-145)."""
+
+    def __init__(self, side1, side2, side3, side4):
+        self.side1 = side1
+        self.side2 = side2
+        self.side3 = side3
+        self.side4 = side4
+
+
+class BaseDefinition(object):
+    """Base class (pyresample/geometry.py:96-140)."""
+
+    def __init__(self, lons=None, lats=None, nprocs=1):
+        if type(lons) is not type(lats):
+            raise TypeError('lons and lats must be of same type')
+        elif lons is not None:
+            if not isinstance(lons, (np.ndarray,)) and not hasattr(lons, "shape"):
+                lons = np.asanyarray(lons)
+                lats = np.asanyarray(lats)
+            if lons.shape != lats.shape:
+                raise ValueError('lons and lats must have same shape')
+        self.nprocs = nprocs
+        self.lons = lons
+        self.lats = lats
+        self.ndim = None
+        self.cartesian_coords = None
+
+    def get_lonlats(self, data_slice=None, chunks=None, **kwargs):
+        """Stored lon/lat arrays, optionally sliced (pyresample/geometry.py:242-274)."""
+        lons, lats = self.lons, self.lats
+        if lons is None or lats is None:
+            raise ValueError('lon/lat values are not defined')
+        if chunks is not None:
+            raise NotImplementedError("dask chunking is not part of the B200 path; arrays are device tensors")
+        if data_slice is not None:
+            lons, lats = lons[data_slice], lats[data_slice]
+        return lons, lats
+
+    def get_boundary_lonlats(self):
+        """Four boundary sides, clockwise from the upper left (pyresample/geometry.py:284-291)."""
+        s1_lon, s1_lat = self.get_lonlats(data_slice=(0, slice(None)))
+        s2_lon, s2_lat = self.get_lonlats(data_slice=(slice(None), -1))
+        s3_lon, s3_lat = self.get_lonlats(data_slice=(-1, slice(None, None, -1)))
+        s4_lon, s4_lat = self.get_lonlats(data_slice=(slice(None, None, -1), 0))
+        return (SimpleBoundary(s1_lon.squeeze(), s2_lon.squeeze(), s3_lon.squeeze(), s4_lon.squeeze()),
+                SimpleBoundary(s1_lat.squeeze(), s2_lat.squeeze(), s3_lat.squeeze(), s4_lat.squeeze()))
+
+    def get_cartesian_coords(self, nprocs=None, data_slice=None, cache=False):
+        """ECEF coordinates on the R=6370997 m sphere, computed on the GPU (pyresample/geometry.py:465-516)."""
+        from . import kd_tree  # late import: needs the CUDA library
+        return kd_tree._cartesian_coords_numpy(self, data_slice)
+
+
+class CoordinateDefinition(BaseDefinition):
+    """Geometry defined by lons and lats only (pyresample/geometry.py:653-700)."""
+
+    def __init__(self, lons, lats, nprocs=1):
+        if not hasattr(lons, "shape") or not hasattr(lons, "dtype"):
+            lons = np.asanyarray(lons)
+            lats = np.asanyarray(lats)
+        super().__init__(lons, lats, nprocs)
+        if tuple(lons.shape) == tuple(lats.shape) and lons.dtype == lats.dtype:
+            self.shape = tuple(lons.shape)
+            self.size = int(np.prod(self.shape)) if len(self.shape) else 1
+            self.ndim = len(self.shape)
+            self.dtype = _np_dtype(lons.dtype)
+        else:
+            raise ValueError(('%s must be created with either '
+                              'lon/lats of the same shape with same dtype') % self.__class__.__name__)
+
+
+class GridDefinition(CoordinateDefinition):
+    """Grid defined by 2-D lons and lats (pyresample/geometry.py:765-810)."""
+
+    def __init__(self, lons, lats, nprocs=1):
+        super().__init__(lons, lats, nprocs)
+        if lons.shape != lats.shape:
+            raise ValueError('lon and lat grid must have same shape')
+        elif lons.ndim != 2:
+            raise ValueError('2 dimensional lon lat grid expected')
+
+
+class SwathDefinition(CoordinateDefinition):
+    """Swath defined by lons and lats (pyresample/geometry.py:813-870)."""
+
+    def __init__(self, lons, lats, nprocs=1, crs=None):
+        super().__init__(lons, lats, nprocs)
+        if lons.shape != lats.shape:
+            raise ValueError('lon and lat arrays must have same shape')
+        elif lons.ndim > 3:
+            raise ValueError('Only 1, 2 or 3 dimensional swaths are allowed')
+        self.crs = crs
+
+
+class AreaDefinition(BaseDefinition):
+    """Uniform grid in a cartographic projection (pyresample/geometry.py:1403-1619).
+
+    ``projection`` is a PROJ.4 dict or string (or a pyproj CRS when pyproj exists).
+    """
+
+    def __init__(self, area_id, description, proj_id, projection, width, height, area_extent, nprocs=1,
+                 lons=None, lats=None, dtype=np.float64):
+        super().__init__(lons, lats, nprocs)
+        self.area_id = area_id
+        self.description = description
+        self.proj_id = proj_id
+        self.width = int(width)
+        self.height = int(height)
+        self.crop_offset = (0, 0)
+        self.shape = (self.height, self.width)
+        self.size = self.height * self.width
+        if lons is not None and tuple(lons.shape) != self.shape:
+            raise ValueError('Shape of lon lat grid must match area definition')
+        self.ndim = 2
+        self.pixel_size_x = (area_extent[2] - area_extent[0]) / float(width)
+        self.pixel_size_y = (area_extent[3] - area_extent[1]) / float(height)
+        self._area_extent = tuple(area_extent)
+        self.proj_dict = proj_to_dict(projection)
+        self.proj_spec = ProjSpec(self.proj_dict)
+        self.upper_left_extent = (float(area_extent[0]), float(area_extent[3]))
+        self.pixel_upper_left = (float(area_extent[0]) + float(self.pixel_size_x) / 2,
+                                 float(area_extent[3]) - float(self.pixel_size_y) / 2)
+        self.pixel_offset_x = -self.area_extent[0] / self.pixel_size_x
+        self.pixel_offset_y = self.area_extent[3] / self.pixel_size_y
+        self.dtype = np.dtype(dtype)
+
+    @property
+    def area_extent(self):
+        return self._area_extent
+
+    @property
+    def proj_str(self):
+        return " ".join("+%s=%s" % (k, v) if v is not True else "+%s" % k for k, v in sorted(self.proj_dict.items()))
+
+    def get_proj_vectors(self, dtype=None, chunks=None):
+        """1-D projection coordinates of the pixel centres (pyresample/geometry.py:1374-1380, 2407-2437).
+
+        Evaluated as ``arange(n, dtype) * pixel_size + offset`` in ``dtype`` with Python-float
+        (weak) scalars, exactly like the reference - SURVEY 9.3.
+        """
+        if dtype is None:
+            dtype = self.dtype
+        x = np.arange(0, self.width, dtype=dtype) * float(self.pixel_size_x) + self.pixel_upper_left[0]
+        y = np.arange(0, self.height, dtype=dtype) * -float(self.pixel_size_y) + self.pixel_upper_left[1]
+        return x, y
+
+    def get_proj_coords(self, data_slice=None, dtype=None, chunks=None):
+        """2-D projection coordinates (pyresample/geometry.py:2449-2488)."""
+        x, y = self.get_proj_vectors(dtype=dtype)
+        ys, xs = _yx_slice(data_slice)
+        if ys is not None:
+            y = y[ys]
+        if xs is not None:
+            x = x[xs]
+        return tuple(np.meshgrid(x, y))
+
+    def get_lonlats(self, nprocs=None, data_slice=None, cache=False, dtype=None, chunks=None):
+        """Lon/lat of the pixel centres, inverse-projected on the GPU (pyresample/geometry.py:2558-2645)."""
+        if dtype is None:
+            dtype = self.dtype
+        if self.lons is not None:
+            lons, lats = self.lons, self.lats
+            if data_slice is not None:
+                lons, lats = lons[data_slice], lats[data_slice]
+            return lons, lats
+        from . import kd_tree  # late import: needs the CUDA library
+        lons, lats = kd_tree._area_lonlats_numpy(self, data_slice, np.dtype(dtype))
+        if cache and data_slice is None:
+            self.lons, self.lats = lons, lats
+        return lons, lats
+
+
+def _yx_slice(data_slice):
+    """AreaDefinition._get_yx_data_slice (pyresample/geometry.py:2491-2496)."""
+    if data_slice is not None and isinstance(data_slice, slice):
+        return data_slice, slice(None, None, None)
+    elif data_slice is not None:
+        return data_slice[0], data_slice[1]
+    return None, None
+
+
+def _get_slice(segments, shape):
+    """Row-block slices (pyresample/geometry.py:3052-3068)."""
+    if not (1 <= len(shape) <= 2):
+        raise ValueError('Cannot segment array of shape: %s' % str(shape))
+    size = shape[0]
+    slice_length = int(np.ceil(float(size) / segments))
+    start_idx = 0
+    end_idx = slice_length
+    while start_idx < size:
+        if len(shape) == 1:
+            yield slice(start_idx, end_idx)
+        else:
+            yield slice(start_idx, end_idx), slice(None)
+        start_idx = end_idx
+        end_idx = min(start_idx + slice_length, size)
+
+
+# --------------------------------------------------------------------------- duck typing
+def _mro_names(obj):
+    return {c.__name__ for c in type(obj).__mro__}
+
+
+def is_base_definition(obj):
+    return isinstance(obj, BaseDefinition) or "BaseDefinition" in _mro_names(obj)
+
+
+def is_area(obj):
+    return isinstance(obj, AreaDefinition) or "AreaDefinition" in _mro_names(obj)
+
+
+def is_griddish(obj):
+    """``isinstance(obj, (GridDefinition, AreaDefinition))`` (pyresample/kd_tree.py:410-412)."""
+    return is_area(obj) or isinstance(obj, GridDefinition) or "GridDefinition" in _mro_names(obj)
+
+
+def is_coord(obj):
+    """``isinstance(obj, CoordinateDefinition)`` (pyresample/kd_tree.py:413)."""
+    return isinstance(obj, CoordinateDefinition) or "CoordinateDefinition" in _mro_names(obj)
+
+
+def is_swath(obj):
+    return isinstance(obj, SwathDefinition) or "SwathDefinition" in _mro_names(obj)
+
+
+def as_geo_def(obj):
+    """Adapt a genuine pyresample geometry object; objects of this module pass through."""
+    if isinstance(obj, BaseDefinition):
+        return obj
+    names = _mro_names(obj)
+    if "AreaDefinition" in names:
+        crs = getattr(obj, "crs", None)
+        projection = crs.to_dict() if crs is not None else obj.proj_dict
+        area = AreaDefinition(getattr(obj, "area_id", ""), getattr(obj, "description", ""),
+                              getattr(obj, "proj_id", ""), projection, obj.width, obj.height, obj.area_extent,
+                              dtype=getattr(obj, "dtype", np.float64))
+        return area
+    if "GridDefinition" in names:
+        return GridDefinition(np.asanyarray(obj.lons), np.asanyarray(obj.lats))
+    if "SwathDefinition" in names:
+        return SwathDefinition(np.asanyarray(obj.lons), np.asanyarray(obj.lats))
+    if "CoordinateDefinition" in names:
+        return CoordinateDefinition(np.asanyarray(obj.lons), np.asanyarray(obj.lats))
+    return obj

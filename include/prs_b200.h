@@ -104,6 +104,8 @@ typedef struct prs_index prs_index; /* opaque spatial index over the valid sourc
 
 int prs_abi_version(void);
 const char *prs_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (measurement aid for bench.py) */
+int64_t prs_launch_count(void);
 
 /* ---- coordinate transform --------------------------------------------------------------------------
  * Cartesian.transform_lonlats (pyresample/_spatial_mp.py:155-169), lonlat2xyz

@@ -25,7 +25,7 @@ PRS_TARGET_LONLAT, PRS_TARGET_AREA = 0, 1
 PRS_REDUCE_ALL, PRS_REDUCE_LAT_GE, PRS_REDUCE_LAT_LE, PRS_REDUCE_BOX, PRS_REDUCE_BOX_DATELINE = 0, 1, 2, 3, 4
 
 EXPORTED_SYMBOLS = (
-    "prs_abi_version", "prs_last_error", "prs_lonlat_to_xyz", "prs_area_lonlats", "prs_valid_mask",
+    "prs_abi_version", "prs_last_error", "prs_launch_count", "prs_lonlat_to_xyz", "prs_area_lonlats", "prs_valid_mask",
     "prs_index_build", "prs_index_destroy", "prs_index_info", "prs_query", "prs_resample_nearest",
     "prs_resample_gauss", "prs_gather_nearest", "prs_gather_weighted", "prs_compact_rows",
     "prs_rank_to_source", "prs_scatter_rows",
@@ -101,6 +101,8 @@ def load_library():
         L.prs_abi_version.argtypes = []
         L.prs_last_error.restype = ctypes.c_char_p
         L.prs_last_error.argtypes = []
+        L.prs_launch_count.restype = ctypes.c_int64
+        L.prs_launch_count.argtypes = []
         L.prs_lonlat_to_xyz.argtypes = [vp, vp, i64, i32, vp, vp]
         L.prs_area_lonlats.argtypes = [ctypes.POINTER(prs_proj_params), ctypes.POINTER(prs_area_grid), i32,
                                        i64, i64, i64, i64, i64, i64, vp, vp, vp, vp]
@@ -120,7 +122,7 @@ def load_library():
         L.prs_rank_to_source.argtypes = [vp, i64, vp, pi64, vp]
         L.prs_scatter_rows.argtypes = [vp, i64, i64, vp, vp, vp, vp]
         for name in EXPORTED_SYMBOLS:
-            if name not in ("prs_abi_version", "prs_last_error"):
+            if name not in ("prs_abi_version", "prs_last_error", "prs_launch_count"):
                 getattr(L, name).restype = i32
         _lib = L
         return L

@@ -334,6 +334,7 @@ extern "C" {
 
 int prs_abi_version(void) { return PRS_ABI_VERSION; }
 const char *prs_last_error(void) { return err_slot().c_str(); }
+int64_t prs_launch_count(void) { return (int64_t)launch_counter(); }
 
 int prs_lonlat_to_xyz(const void *lon, const void *lat, int64_t n, int dtype, void *xyz_out, void *stream)
 {

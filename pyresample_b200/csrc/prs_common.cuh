@@ -34,7 +34,16 @@ inline int fail(int code, const std::string &msg)
             return prs::fail(PRS_ECUDA, _b);                                                             \
         }                                                                                                \
     } while (0)
-#define PRS_CKL() PRS_CK(cudaGetLastError())
+inline long long &launch_counter()
+{
+    static long long n = 0;  // kernels launched by this library (bench.py's gpu_launches); not thread-exact
+    return n;
+}
+#define PRS_CKL()                      \
+    do {                               \
+        ++prs::launch_counter();       \
+        PRS_CK(cudaGetLastError());    \
+    } while (0)
 
 // ------------------------------------------------------------------------------------------ arithmetic
 // All distance / ECEF arithmetic uses explicit round-to-nearest intrinsics so that nvcc never contracts

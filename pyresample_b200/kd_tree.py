@@ -85,6 +85,15 @@ def _dev(x, dtype=None):
     return t.contiguous()
 
 
+def _host(t):
+    """CUDA tensor -> numpy array through a pinned staging buffer (torch's caching host allocator)."""
+    torch = _torch()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()
+
+
 def _tree_code(np_dtype):
     np_dtype = np.dtype(np_dtype)
     if np_dtype == np.float32:
@@ -467,8 +476,8 @@ def get_neighbour_info(source_geo_def, target_geo_def, radius_of_influence,
         idx = _compact_rows(valid, idx)
         dist = _compact_rows(valid, dist)
     valid_output_index = valid.cpu().numpy().astype(bool)
-    index_array = idx.cpu().numpy().view(np.uint32)
-    distance_array = dist.cpu().numpy()
+    index_array = _host(idx).view(np.uint32)
+    distance_array = _host(dist)
     if neighbours == 1:
         index_array = index_array.reshape(-1)
         distance_array = distance_array.reshape(-1)
@@ -666,7 +675,7 @@ def get_sample_from_neighbour_info(resample_type, output_shape, data,
         _cabi.check(L.prs_gather_nearest(_ptr(idx_t), n_out, int(valid_input_size), _ptr(rank_to_source),
                                          _ptr(dev_data), row_bytes, _ptr(fill_row), _ptr(res_t), _stream()))
         res_t = _scatter_full(res_t, voi_t, output_size, fill_row)
-        result = res_t.cpu().numpy().view(new_data.dtype)
+        result = _host(res_t).view(new_data.dtype)
         if with_uncert:
             stddev = count = None
     else:
@@ -683,7 +692,7 @@ def get_sample_from_neighbour_info(resample_type, output_shape, data,
                                                  with_uncert, dist_np)
         fill_row = torch.full((channels,), float(fill_value), dtype=res_t.dtype, device="cuda")
         res_t = _scatter_full(res_t, voi_t, output_size, fill_row)
-        result = res_t.cpu().numpy().astype(rt, copy=False)
+        result = _host(res_t).astype(rt, copy=False)
         if with_uncert:
             nan_row = torch.full((channels,), float("nan"), dtype=sd_t.dtype, device="cuda")
             zero_row = torch.zeros((channels,), dtype=cnt_t.dtype, device="cuda")
@@ -788,8 +797,12 @@ def _weighted_from_info(idx_t, dist_t, n_out, k, n_valid, rank_to_source, dev_da
 # =========================================================================================== fused resampling
 def _resample(source_geo_def, data, target_geo_def, resample_type,
               radius_of_influence, neighbours=8, epsilon=0, weight_funcs=None,
-              fill_value=0, reduce_data=True, nprocs=1, segments=None, with_uncert=False):
-    """Resample using the kd-tree approach (pyresample/kd_tree.py:256-278), fused on the GPU when possible."""
+              fill_value=0, reduce_data=True, nprocs=1, segments=None, with_uncert=False, _rows=None):
+    """Resample using the kd-tree approach (pyresample/kd_tree.py:256-278), fused on the GPU when possible.
+
+    ``_rows=(row0, nrows)`` restricts the output to one row block of the target (multi-GPU sharding,
+    pyresample_b200/distributed.py); the source mask and index are those of the whole target.
+    """
     if source_geo_def.size < neighbours:
         warnings.warn('Searching for %s neighbours in %s data points' %
                       (neighbours, source_geo_def.size), stacklevel=3)
@@ -800,7 +813,9 @@ def _resample(source_geo_def, data, target_geo_def, resample_type,
     n_src = int(source.lon_t.numel())
     if tensor_io:
         return _resample_tensor(source, data, tgt, resample_type, radius_of_influence, neighbours, weight_funcs,
-                                fill_value, reduce_data, with_uncert)
+                                fill_value, reduce_data, with_uncert, _rows)
+    if _rows is not None:
+        raise NotImplementedError("row-block resampling is implemented for CUDA tensor inputs")
     data = _flatten_data(data, n_src)
     is_multi_channel = data.ndim > 1
     if source.index is None:
@@ -846,7 +861,7 @@ def _resample(source_geo_def, data, target_geo_def, resample_type,
         out = torch.empty((n_t, row_bytes), dtype=torch.uint8, device="cuda")
         _cabi.check(L.prs_resample_nearest(source.index.handle, ctypes.byref(tg), float(radius_of_influence),
                                            _ptr(dev_data), row_bytes, _ptr(fill_row), _ptr(out), _stream()))
-        result = out.cpu().numpy().view(new_data.dtype)
+        result = _host(out).view(new_data.dtype)
         if with_uncert:
             raise TypeError("uncertainty estimates need more than one neighbour")
     else:
@@ -896,7 +911,7 @@ def _resample(source_geo_def, data, target_geo_def, resample_type,
         if kth_found:
             warnings.warn(('Possible more than %s neighbours within %s m for some data points') %
                           (neighbours, radius_of_influence), stacklevel=3)
-        result = out.cpu().numpy().astype(rt, copy=False)
+        result = _host(out).astype(rt, copy=False)
         if with_uncert:
             stddev, count = sd_t.cpu().numpy(), cnt_t.cpu().numpy()
     del keep
@@ -918,7 +933,7 @@ def _rank_to_source(source):
 
 
 def _resample_tensor(source, data, tgt, resample_type, radius_of_influence, neighbours, weight_funcs, fill_value,
-                     reduce_data, with_uncert):
+                     reduce_data, with_uncert, rows=None):
     """Device-resident variant: CUDA tensor in -> CUDA tensor out (no host copies, no masked arrays)."""
     torch = _torch()
     L = _cabi.lib()
@@ -932,12 +947,14 @@ def _resample_tensor(source, data, tgt, resample_type, radius_of_influence, neig
         raise ValueError('Mismatch between geometry and dataset')
     multi = data.dim() > 1
     channels = data.shape[1] if multi else 1
-    output_shape = tuple(tgt.shape) + ((channels,) if multi else ())
+    row0, nrows = (0, None) if rows is None else (int(rows[0]), int(rows[1]))
+    lead = tuple(tgt.shape) if rows is None else (nrows,) + tuple(tgt.shape[1:])
+    output_shape = lead + ((channels,) if multi else ())
     if fill_value is None:
         raise ValueError("fill_value=None (masked output) needs numpy input")
     if source.index is None:
         return torch.full(output_shape, fill_value, dtype=data.dtype, device="cuda")
-    tg, n_t, keep = _make_target(source, tgt, reduce_data, radius_of_influence)
+    tg, n_t, keep = _make_target(source, tgt, reduce_data, radius_of_influence, row0, nrows)
     dev_data = data.contiguous().reshape(n_src, -1)
     if resample_type == 'nn':
         row_bytes = dev_data.shape[1] * dev_data.element_size()

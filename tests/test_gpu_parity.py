@@ -307,7 +307,8 @@ def test_reference_gauss_5000x100(kd, geometry):
         res = kd.resample_gauss(swath_def, data.ravel(), area_def, 50000, 25000, segments=1)
         assert len(w) == 1 and 'Possible more' in str(w[0].message)
     assert res.sum() == pytest.approx(4872.8100353517921, rel=1e-9)  # test_kd_tree.py:287-317
-    data_multi = np.column_stack((data.ravel(), data.ravel(), data.ravel()))
+    data6 = np.fromfunction(lambda y, x: (y + x) * 10 ** -6, (5000, 100))
+    data_multi = np.column_stack((data6.ravel(), data6.ravel(), data6.ravel()))
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         res = kd.resample_gauss(swath_def, data_multi, area_def, 50000, [25000, 15000, 10000], segments=1)

@@ -248,6 +248,8 @@ template <typename T> int launch_query_t(QueryParams &P, const prs_index *index,
     ix.cell_start = index->cell_start;
     ix.coarse_start = index->coarse_start;
     ix.rank = index->rank;
+    ix.fine = index->fine;
+    ix.coarse = index->coarse;
     ix.G = index->G;
     ix.Gc = index->Gc;
     ix.n_valid = (uint32_t)index->n_valid;
@@ -436,10 +438,11 @@ int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, cons
 int prs_index_destroy(prs_index *ix)
 {
     if (!ix) return PRS_OK;
-    if (ix->recs) cudaFree(ix->recs);
-    if (ix->cell_start) cudaFree(ix->cell_start);
-    if (ix->coarse_start) cudaFree(ix->coarse_start);
-    if (ix->rank) cudaFree(ix->rank);
+    // stream-ordered: blocks return to the pool once the work already queued on the build stream has finished
+    if (ix->recs) cudaFreeAsync(ix->recs, ix->stream);
+    if (ix->cell_start) cudaFreeAsync(ix->cell_start, ix->stream);
+    if (ix->coarse_start) cudaFreeAsync(ix->coarse_start, ix->stream);
+    if (ix->rank) cudaFreeAsync(ix->rank, ix->stream);
     delete ix;
     return PRS_OK;
 }

@@ -1,8 +1,31 @@
 // Spatial index over the valid source points: cube-face cell grid built by a counting sort
 // (one-digit radix sort on the cell key), replacing pykdtree.KDTree(input_coords) (kd_tree.py:464-489).
+//
+// Layout in HBM
+//   recs[n_indexed]      Rec<T> = ECEF xyz in the tree dtype + raveled source index, sorted by cell key
+//   cell_start[M + 1]    prefix sums over the cell table.  The table only spans, per cube face, the bounding
+//                        rectangle of the cells that can hold a point (from an occupancy probe), row-major:
+//                        key = face_base[f] + (iv - fv0[f]) * fw[f] + (iu - fu0[f])
+//   coarse_start[Mc + 1] the same for COARSE x COARSE blocks of cells (L2-resident; answers "is there any
+//                        source point within the radius at all" for the many target pixels far from the swath)
+//   rank[n_source]       rank of every source point among the valid ones (omitted when all are valid)
 #pragma once
 #include "prs_common.cuh"
 #include "prs_scan.cuh"
+
+namespace prs {
+
+constexpr int COARSE = 16;   // fine cells per coarse cell side
+constexpr int OCC_G = 128;   // resolution of the occupancy probe used to size the cells and the table
+constexpr uint32_t CELL_SKIP = 0xFFFFFFFFu;
+
+// Per-face table geometry (fine and coarse).  A face without points has fw == 0.
+struct FaceTable {
+    int fu0[6], fv0[6], fw[6], fh[6];
+    int64_t base[6];
+};
+
+}  // namespace prs
 
 struct prs_index {
     int tree_dtype;      // PRS_F32 / PRS_F64
@@ -13,57 +36,119 @@ struct prs_index {
     int Gc;              // coarse cells per face side
     int all_valid;       // rank == source index
     uint32_t first_valid_source;  // raveled index of rank 0 (kd_tree.py:754-759 gathers new_data[0] for missing)
-    void *recs;          // Rec<T>[n_indexed], sorted by cell
-    uint32_t *cell_start;    // [6*G*G + 1]
-    uint32_t *coarse_start;  // [6*Gc*Gc + 1]
-    uint32_t *rank;          // [n_source] rank of each source point (NULL when all_valid)
+    void *recs;
+    uint32_t *cell_start;
+    uint32_t *coarse_start;
+    uint32_t *rank;
+    prs::FaceTable fine, coarse;
+    int64_t n_cells, n_coarse;
     size_t bytes;
+    cudaStream_t stream;  // stream the memory was allocated on (stream-ordered free)
 };
 
 namespace prs {
 
-constexpr int COARSE = 16;       // fine cells per coarse cell side
-constexpr int OCC_G = 128;       // resolution of the occupancy probe used to size the cells
-constexpr uint32_t CELL_SKIP = 0xFFFFFFFFu;
-
-template <typename T> __device__ __forceinline__ uint32_t cell_of(T x, T y, T z, int G)
+// Stream-ordered allocations come from the device's default pool; keep freed blocks cached in the pool
+// instead of returning them to the driver (cudaMalloc/cudaFree of the 100 MB-class tables costs tens of ms).
+inline int ensure_pool_configured()
 {
-    int face;
-    float u, v;
-    const float invR = (float)(1.0 / PRS_R);
-    face_uv((float)x * invR, (float)y * invR, (float)z * invR, face, u, v);
-    int iu = cell_coord(warp_uv(u), G), iv = cell_coord(warp_uv(v), G);
-    return (uint32_t)((face * G + iv) * G + iu);
+    static bool done = false;
+    if (done) return PRS_OK;
+    int dev = 0;
+    PRS_CK(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    PRS_CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long thr = ~0ull;
+    PRS_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    done = true;
+    return PRS_OK;
 }
+
+__device__ __forceinline__ void face_cell_of(float x, float y, float z, int G, int &face, int &iu, int &iv)
+{
+    float u, v;
+    face_uv(x, y, z, face, u, v);
+    iu = cell_coord(warp_uv(u), G);
+    iv = cell_coord(warp_uv(v), G);
+}
+
+template <typename T> __device__ __forceinline__ void unit_f32(T x, T y, T z, float &fx, float &fy, float &fz)
+{
+    const float invR = (float)(1.0 / PRS_R);
+    fx = (float)x * invR;
+    fy = (float)y * invR;
+    fz = (float)z * invR;
+}
+
+struct BuildCounters {
+    uint32_t n_valid;
+    uint32_t n_excluded;
+    uint32_t first_source;
+    uint32_t pad;
+};
 
 // Pass 1: ECEF of every valid point, written in rank order; occupancy probe at OCC_G resolution.
 template <typename T>
 __global__ void build_xyz_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n,
                                  const uint8_t *__restrict__ valid, const uint8_t *__restrict__ exclude,
                                  const uint32_t *__restrict__ rank, Rec<T> *__restrict__ tmp,
-                                 uint32_t *__restrict__ cellid, uint8_t *__restrict__ occ)
+                                 uint32_t *__restrict__ cellid, uint8_t *__restrict__ occ, BuildCounters *counters)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !valid[i]) return;
-    uint32_t r = rank ? rank[i] : (uint32_t)i;
+    uint32_t r = rank[i];
     T x, y, z;
     lonlat_to_xyz(lon[i], lat[i], x, y, z);
     store_rec(tmp + r, x, y, z, (uint32_t)i);
+    if (r == 0) counters->first_source = (uint32_t)i;
     bool skip = exclude && exclude[i];
     cellid[r] = skip ? CELL_SKIP : 0u;
-    if (!skip) occ[cell_of(x, y, z, OCC_G)] = 1;
+    if (skip) {
+        atomicAdd(&counters->n_excluded, 1u);
+    } else {
+        float fx, fy, fz;
+        unit_f32<T>(x, y, z, fx, fy, fz);
+        int face, iu, iv;
+        face_cell_of(fx, fy, fz, OCC_G, face, iu, iv);
+        occ[(face * OCC_G + iv) * OCC_G + iu] = 1;
+    }
 }
 
-// Pass 2: cell key of every indexed point + histogram into table[cell + 1].
+// Bounding rectangle (in probe cells) of the occupied probe cells of each face: rect[f] = {u0, v0, u1, v1}.
+__global__ void occ_rect_kernel(const uint8_t *__restrict__ occ, int *__restrict__ rect, uint32_t *__restrict__ n_occ)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6 * OCC_G * OCC_G || !occ[i]) return;
+    int f = i / (OCC_G * OCC_G), iv = (i / OCC_G) % OCC_G, iu = i % OCC_G;
+    atomicMin(&rect[4 * f + 0], iu);
+    atomicMin(&rect[4 * f + 1], iv);
+    atomicMax(&rect[4 * f + 2], iu);
+    atomicMax(&rect[4 * f + 3], iv);
+    atomicAdd(n_occ, 1u);
+}
+
+__device__ __forceinline__ int64_t table_key(const FaceTable &t, int face, int iu, int iv)
+{
+    return t.base[face] + (int64_t)(iv - t.fv0[face]) * t.fw[face] + (iu - t.fu0[face]);
+}
+
+// Pass 2: cell key of every indexed point + histogram into table[key + 1].
 template <typename T>
-__global__ void build_count_kernel(const Rec<T> *__restrict__ tmp, int64_t n_valid, int G,
+__global__ void build_count_kernel(const Rec<T> *__restrict__ tmp, int64_t n_valid, int G, const FaceTable ft,
                                    uint32_t *__restrict__ cellid, uint32_t *__restrict__ table)
 {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_valid) return;
     if (cellid[j] == CELL_SKIP) return;
     Rec<T> r = load_rec(tmp + j);
-    uint32_t c = cell_of(r.x, r.y, r.z, G);
+    float fx, fy, fz;
+    unit_f32<T>(r.x, r.y, r.z, fx, fy, fz);
+    int face, iu, iv;
+    face_cell_of(fx, fy, fz, G, face, iu, iv);
+    // the table rectangle is a superset of the probe cells by construction; clamp defensively
+    iu = min(max(iu, ft.fu0[face]), ft.fu0[face] + ft.fw[face] - 1);
+    iv = min(max(iv, ft.fv0[face]), ft.fv0[face] + ft.fh[face] - 1);
+    uint32_t c = (uint32_t)table_key(ft, face, iu, iv);
     cellid[j] = c;
     atomicAdd(&table[c + 1], 1u);
 }
@@ -83,40 +168,23 @@ __global__ void build_scatter_kernel(const Rec<T> *__restrict__ tmp, int64_t n_v
     store_rec(recs + pos, r.x, r.y, r.z, r.idx);
 }
 
-// Within a cell the scatter order depends on atomic arrival; sort each cell by source index so the
-// layout (not just the result) is deterministic.  Cells hold a handful of points: insertion sort.
-template <typename T>
-__global__ void build_sort_cells_kernel(Rec<T> *__restrict__ recs, const uint32_t *__restrict__ cell_start,
-                                        int64_t n_cells)
-{
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cells) return;
-    uint32_t s = cell_start[c], e = cell_start[c + 1];
-    for (uint32_t i = s + 1; i < e; ++i) {
-        Rec<T> key = recs[i];
-        uint32_t j = i;
-        while (j > s && recs[j - 1].idx > key.idx) {
-            recs[j] = recs[j - 1];
-            --j;
-        }
-        recs[j] = key;
-    }
-}
-
 // Coarse table: number of points in each COARSE x COARSE block of fine cells, from the fine row prefix sums.
-__global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_start, int G, int Gc,
-                                    uint32_t *__restrict__ ctable)
+__global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_start, const FaceTable fine, const FaceTable coarse,
+                                    int64_t n_coarse, uint32_t *__restrict__ ctable)
 {
     int64_t cc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t ncc = 6LL * Gc * Gc;
-    if (cc >= ncc) return;
-    int cu = (int)(cc % Gc);
-    int cv = (int)((cc / Gc) % Gc);
-    int face = (int)(cc / ((int64_t)Gc * Gc));
+    if (cc >= n_coarse) return;
+    int face = 5;
+#pragma unroll
+    for (int f = 4; f >= 0; --f)
+        if (cc < coarse.base[f + 1]) face = f;
+    int64_t local = cc - coarse.base[face];
+    int cu = coarse.fu0[face] + (int)(local % coarse.fw[face]);
+    int cv = coarse.fv0[face] + (int)(local / coarse.fw[face]);
     uint32_t tot = 0;
     for (int r = 0; r < COARSE; ++r) {
-        int64_t row = ((int64_t)face * G + (cv * COARSE + r)) * G;
-        tot += cell_start[row + cu * COARSE + COARSE] - cell_start[row + cu * COARSE];
+        int64_t k0 = table_key(fine, face, cu * COARSE, cv * COARSE + r);
+        tot += cell_start[k0 + COARSE] - cell_start[k0];
     }
     ctable[cc + 1] = tot;
 }
@@ -127,65 +195,81 @@ int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, c
 {
     (void)radius_hint;
     const int TPB = 256;
-    // ranks of valid points
-    uint32_t *rank = nullptr, *tot_dev = nullptr;
-    PRS_CK(cudaMalloc((void **)&rank, sizeof(uint32_t) * (size_t)n));
-    PRS_CK(cudaMallocAsync((void **)&tot_dev, sizeof(uint32_t) * 2, st));
-    int rc = scan_u32<uint8_t>(valid, rank, n, 0, tot_dev, st);
+    int rc = ensure_pool_configured();
     if (rc != PRS_OK) return rc;
-    uint32_t n_valid_h = 0;
-    PRS_CK(cudaMemcpyAsync(&n_valid_h, tot_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PRS_CK(cudaStreamSynchronize(st));
-    ix->n_valid = n_valid_h;
-    ix->all_valid = (int64_t)n_valid_h == n;
+    ix->stream = st;
+    // ranks of valid points (numpy's boolean compaction order)
+    uint32_t *rank = nullptr;
+    BuildCounters *counters = nullptr;
+    PRS_CK(cudaMallocAsync((void **)&rank, sizeof(uint32_t) * (size_t)n, st));
     ix->rank = rank;
     ix->bytes += sizeof(uint32_t) * (size_t)n;
-    if (ix->all_valid) {
-        PRS_CK(cudaFree(rank));
-        ix->rank = rank = nullptr;
+    const size_t occ_n = 6ull * OCC_G * OCC_G;
+    // scratch block: counters | n_occ | rect[24] | occ[occ_n]
+    uint8_t *scratch = nullptr;
+    const size_t scratch_bytes = 256 + occ_n;
+    PRS_CK(cudaMallocAsync((void **)&scratch, scratch_bytes, st));
+    PRS_CK(cudaMemsetAsync(scratch, 0, scratch_bytes, st));
+    counters = (BuildCounters *)scratch;
+    uint32_t *n_occ_dev = (uint32_t *)(scratch + 16);
+    int *rect_dev = (int *)(scratch + 32);
+    uint8_t *occ = scratch + 256;
+    {
+        int init[24];
+        for (int f = 0; f < 6; ++f) {
+            init[4 * f] = init[4 * f + 1] = 1 << 30;
+            init[4 * f + 2] = init[4 * f + 3] = -1;
+        }
+        PRS_CK(cudaMemcpyAsync(rect_dev, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
+    rc = scan_u32<uint8_t>(valid, rank, n, 0, &counters->n_valid, st);
+    if (rc != PRS_OK) return rc;
+    // pass 1 (sized by the upper bound n so that no host round trip is needed first)
+    Rec<T> *tmp = nullptr;
+    uint32_t *cellid = nullptr;
+    PRS_CK(cudaMallocAsync((void **)&tmp, sizeof(Rec<T>) * (size_t)n, st));
+    PRS_CK(cudaMallocAsync((void **)&cellid, sizeof(uint32_t) * (size_t)n, st));
+    build_xyz_kernel<T><<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, st>>>(lon, lat, n, valid, exclude, rank, tmp, cellid,
+                                                                          occ, counters);
+    PRS_CKL();
+    occ_rect_kernel<<<(unsigned)((occ_n + TPB - 1) / TPB), TPB, 0, st>>>(occ, rect_dev, n_occ_dev);
+    PRS_CKL();
+    // the one host round trip of the build: sizes the cell grid
+    struct {
+        BuildCounters c;
+        uint32_t n_occ;
+        uint32_t pad[3];
+        int rect[24];
+    } h;
+    PRS_CK(cudaMemcpyAsync(&h, scratch, sizeof(h), cudaMemcpyDeviceToHost, st));
+    PRS_CK(cudaStreamSynchronize(st));
+    PRS_CK(cudaFreeAsync(scratch, st));
+    ix->n_valid = h.c.n_valid;
+    ix->n_indexed = (int64_t)h.c.n_valid - (int64_t)h.c.n_excluded;
+    ix->first_valid_source = h.c.first_source;
+    ix->all_valid = (int64_t)h.c.n_valid == n;
+    if (ix->all_valid) {  // rank == source index: the table is not needed by queries
+        PRS_CK(cudaFreeAsync(rank, st));
+        ix->rank = nullptr;
         ix->bytes -= sizeof(uint32_t) * (size_t)n;
     }
-    if (n_valid_h == 0) {
-        PRS_CK(cudaFreeAsync(tot_dev, st));
+    if (ix->n_indexed <= 0) {
+        PRS_CK(cudaFreeAsync(tmp, st));
+        PRS_CK(cudaFreeAsync(cellid, st));
         ix->n_indexed = 0;
         ix->G = COARSE;
         ix->Gc = 1;
         return PRS_OK;
     }
-    // pass 1
-    Rec<T> *tmp = nullptr;
-    uint32_t *cellid = nullptr;
-    uint8_t *occ = nullptr;
-    const size_t occ_n = 6ull * OCC_G * OCC_G;
-    PRS_CK(cudaMallocAsync((void **)&tmp, sizeof(Rec<T>) * (size_t)n_valid_h, st));
-    PRS_CK(cudaMallocAsync((void **)&cellid, sizeof(uint32_t) * (size_t)n_valid_h, st));
-    PRS_CK(cudaMallocAsync((void **)&occ, occ_n, st));
-    PRS_CK(cudaMemsetAsync(occ, 0, occ_n, st));
-    build_xyz_kernel<T><<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, st>>>(lon, lat, n, valid, exclude, rank, tmp,
-                                                                          cellid, occ);
-    PRS_CKL();
-    // first valid source index + occupancy -> cell resolution
-    uint32_t *occ_sum = nullptr;
-    PRS_CK(cudaMallocAsync((void **)&occ_sum, sizeof(uint32_t) * occ_n, st));
-    rc = scan_u32<uint8_t>(occ, occ_sum, (int64_t)occ_n, 1, tot_dev + 1, st);
-    if (rc != PRS_OK) return rc;
-    uint32_t n_occ = 0;
-    Rec<T> first;
-    PRS_CK(cudaMemcpyAsync(&n_occ, tot_dev + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PRS_CK(cudaMemcpyAsync(&first, tmp, sizeof(Rec<T>), cudaMemcpyDeviceToHost, st));
-    PRS_CK(cudaStreamSynchronize(st));
-    PRS_CK(cudaFreeAsync(occ_sum, st));
-    PRS_CK(cudaFreeAsync(occ, st));
-    ix->first_valid_source = first.idx;
     double lambda = k_hint > 4 ? (double)k_hint : 4.0;  // target points per cell
     if (const char *env = getenv("PRS_CELL_OCCUPANCY")) {
         double v = atof(env);
         if (v > 0) lambda = v;
     }
-    if (n_occ == 0) n_occ = 1;
-    double g = (double)OCC_G * sqrt((double)n_valid_h / ((double)n_occ * lambda));
+    uint32_t n_occ = h.n_occ ? h.n_occ : 1;
+    double g = (double)OCC_G * sqrt((double)ix->n_indexed / ((double)n_occ * lambda));
     int G = (int)ceil(g / COARSE) * COARSE;
-    int Gmax = 8192;
+    int Gmax = 16384;
     if (const char *env = getenv("PRS_MAX_CELLS_PER_SIDE")) {
         int v = atoi(env);
         if (v >= COARSE) Gmax = (v / COARSE) * COARSE;
@@ -194,41 +278,65 @@ int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, c
     if (G > Gmax) G = Gmax;
     ix->G = G;
     ix->Gc = G / COARSE;
+    // table rectangles: probe rect -> coarse cells (conservative, +1 probe cell of slack) -> fine cells
+    int64_t nf = 0, nc = 0;
+    for (int f = 0; f < 6; ++f) {
+        const int *r = h.rect + 4 * f;
+        ix->fine.base[f] = nf;
+        ix->coarse.base[f] = nc;
+        if (r[2] < r[0]) {
+            ix->fine.fu0[f] = ix->fine.fv0[f] = ix->fine.fw[f] = ix->fine.fh[f] = 0;
+            ix->coarse.fu0[f] = ix->coarse.fv0[f] = ix->coarse.fw[f] = ix->coarse.fh[f] = 0;
+            continue;
+        }
+        auto lo = [&](int p) { long v = (long)floor((double)(p - 1) * ix->Gc / OCC_G); return (int)(v < 0 ? 0 : v); };
+        auto hi = [&](int p) {
+            long v = (long)ceil((double)(p + 2) * ix->Gc / OCC_G);
+            return (int)(v > ix->Gc ? ix->Gc : v);
+        };
+        int cu0 = lo(r[0]), cv0 = lo(r[1]), cu1 = hi(r[2]), cv1 = hi(r[3]);  // [cu0, cu1) coarse cells
+        if (cu1 <= cu0) cu1 = cu0 + 1;
+        if (cv1 <= cv0) cv1 = cv0 + 1;
+        ix->coarse.fu0[f] = cu0;
+        ix->coarse.fv0[f] = cv0;
+        ix->coarse.fw[f] = cu1 - cu0;
+        ix->coarse.fh[f] = cv1 - cv0;
+        ix->fine.fu0[f] = cu0 * COARSE;
+        ix->fine.fv0[f] = cv0 * COARSE;
+        ix->fine.fw[f] = (cu1 - cu0) * COARSE;
+        ix->fine.fh[f] = (cv1 - cv0) * COARSE;
+        nc += (int64_t)ix->coarse.fw[f] * ix->coarse.fh[f];
+        nf += (int64_t)ix->fine.fw[f] * ix->fine.fh[f];
+    }
+    ix->n_cells = nf;
+    ix->n_coarse = nc;
+    if (nf >= 0xFFFFFFF0LL) return fail(PRS_ENOSUP, "cell table too large");
     // pass 2 + scan + pass 3
-    const int64_t n_cells = 6LL * G * G;
-    PRS_CK(cudaMalloc((void **)&ix->cell_start, sizeof(uint32_t) * (size_t)(n_cells + 1)));
-    ix->bytes += sizeof(uint32_t) * (size_t)(n_cells + 1);
-    PRS_CK(cudaMemsetAsync(ix->cell_start, 0, sizeof(uint32_t) * (size_t)(n_cells + 1), st));
-    unsigned gv = (unsigned)(((int64_t)n_valid_h + TPB - 1) / TPB);
-    build_count_kernel<T><<<gv, TPB, 0, st>>>(tmp, n_valid_h, G, cellid, ix->cell_start);
+    PRS_CK(cudaMallocAsync((void **)&ix->cell_start, sizeof(uint32_t) * (size_t)(nf + 1), st));
+    ix->bytes += sizeof(uint32_t) * (size_t)(nf + 1);
+    PRS_CK(cudaMemsetAsync(ix->cell_start, 0, sizeof(uint32_t) * (size_t)(nf + 1), st));
+    unsigned gv = (unsigned)((ix->n_valid + TPB - 1) / TPB);
+    build_count_kernel<T><<<gv, TPB, 0, st>>>(tmp, ix->n_valid, G, ix->fine, cellid, ix->cell_start);
     PRS_CKL();
-    rc = scan_u32<uint32_t>(ix->cell_start + 1, ix->cell_start + 1, n_cells, 0, tot_dev, st);
+    rc = scan_u32<uint32_t>(ix->cell_start + 1, ix->cell_start + 1, nf, 0, nullptr, st);
     if (rc != PRS_OK) return rc;
-    uint32_t n_idx_h = 0;
-    PRS_CK(cudaMemcpyAsync(&n_idx_h, tot_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PRS_CK(cudaStreamSynchronize(st));
-    ix->n_indexed = n_idx_h;
-    size_t rec_bytes = sizeof(Rec<T>) * (size_t)(n_idx_h > 0 ? n_idx_h : 1);
-    PRS_CK(cudaMalloc((void **)&ix->recs, rec_bytes));
+    size_t rec_bytes = sizeof(Rec<T>) * (size_t)ix->n_indexed;
+    PRS_CK(cudaMallocAsync((void **)&ix->recs, rec_bytes, st));
     ix->bytes += rec_bytes;
-    build_scatter_kernel<T><<<gv, TPB, 0, st>>>(tmp, n_valid_h, cellid, ix->cell_start, (Rec<T> *)ix->recs);
-    PRS_CKL();
-    build_sort_cells_kernel<T><<<(unsigned)((n_cells + TPB - 1) / TPB), TPB, 0, st>>>((Rec<T> *)ix->recs,
-                                                                                      ix->cell_start, n_cells);
+    build_scatter_kernel<T><<<gv, TPB, 0, st>>>(tmp, ix->n_valid, cellid, ix->cell_start, (Rec<T> *)ix->recs);
     PRS_CKL();
     // coarse table
-    const int64_t n_cc = 6LL * ix->Gc * ix->Gc;
-    PRS_CK(cudaMalloc((void **)&ix->coarse_start, sizeof(uint32_t) * (size_t)(n_cc + 1)));
-    ix->bytes += sizeof(uint32_t) * (size_t)(n_cc + 1);
+    PRS_CK(cudaMallocAsync((void **)&ix->coarse_start, sizeof(uint32_t) * (size_t)(nc + 1), st));
+    ix->bytes += sizeof(uint32_t) * (size_t)(nc + 1);
     PRS_CK(cudaMemsetAsync(ix->coarse_start, 0, sizeof(uint32_t), st));
-    build_coarse_kernel<<<(unsigned)((n_cc + TPB - 1) / TPB), TPB, 0, st>>>(ix->cell_start, G, ix->Gc,
-                                                                          ix->coarse_start);
+    FaceTable cb = ix->coarse;  // build_coarse_kernel reads base[f + 1]: keep a sentinel in a local copy
+    build_coarse_kernel<<<(unsigned)((nc + TPB - 1) / TPB), TPB, 0, st>>>(ix->cell_start, ix->fine, cb, nc,
+                                                                         ix->coarse_start);
     PRS_CKL();
-    rc = scan_u32<uint32_t>(ix->coarse_start + 1, ix->coarse_start + 1, n_cc, 1, nullptr, st);
+    rc = scan_u32<uint32_t>(ix->coarse_start + 1, ix->coarse_start + 1, nc, 1, nullptr, st);
     if (rc != PRS_OK) return rc;
     PRS_CK(cudaFreeAsync(tmp, st));
     PRS_CK(cudaFreeAsync(cellid, st));
-    PRS_CK(cudaFreeAsync(tot_dev, st));
     return PRS_OK;
 }
 

@@ -46,6 +46,7 @@ template <typename T> struct IndexView {
     const uint32_t *cell_start;
     const uint32_t *coarse_start;
     const uint32_t *rank;  // NULL when rank == source index
+    FaceTable fine, coarse;
     int G, Gc;
     uint32_t n_valid;
     uint32_t first_valid_source;
@@ -55,6 +56,17 @@ template <typename T> struct IndexView {
 struct CellRect {
     int u0, u1, v0, v1;
 };
+
+// Intersect with the part of the face the table spans; false when nothing is left.
+__device__ __forceinline__ bool clip_rect(const FaceTable &t, int face, CellRect &r)
+{
+    if (t.fw[face] == 0) return false;
+    r.u0 = max(r.u0, t.fu0[face]);
+    r.u1 = min(r.u1, t.fu0[face] + t.fw[face] - 1);
+    r.v0 = max(r.v0, t.fv0[face]);
+    r.v1 = min(r.v1, t.fv0[face] + t.fh[face] - 1);
+    return r.u0 <= r.u1 && r.v0 <= r.v1;
+}
 
 // (fx, fy, fz): unit query vector.  s2: upper bound of sin^2 of the cap's angular radius.
 // Returns false when the cap cannot touch this face.  Closed form: the gnomonic image of a spherical cap is
@@ -113,6 +125,23 @@ template <typename T> __device__ __forceinline__ float cap_s2(T d2)
     return (float)d2 * invR2 * 1.0002f + 1e-13f;
 }
 
+// Number of indexed points inside the cap's cell rectangles of the COARSE table (an upper bound of the number of
+// points within the cap; 0 proves there is none).
+__device__ __forceinline__ uint32_t coarse_count(const FaceTable &ct, const uint32_t *__restrict__ coarse_start, int Gc,
+                                                 float fx, float fy, float fz, float s2, float s)
+{
+    uint32_t total = 0;
+#pragma unroll 1
+    for (int f = 0; f < 6; ++f) {
+        CellRect c;
+        if (!face_rect(f, fx, fy, fz, s2, s, Gc, c)) continue;
+        if (!clip_rect(ct, f, c)) continue;
+        const uint32_t *row = coarse_start + ct.base[f] + (int64_t)(c.v0 - ct.fv0[f]) * ct.fw[f] - ct.fu0[f];
+        for (int iv = c.v0; iv <= c.v1; ++iv, row += ct.fw[f]) total += __ldg(row + c.u1 + 1) - __ldg(row + c.u0);
+    }
+    return total;
+}
+
 template <typename T, int K>
 __device__ __forceinline__ void scan_run(const Rec<T> *__restrict__ recs, uint32_t s, uint32_t e, T qx, T qy, T qz,
                                          T dub, TopK<T, K> &top)
@@ -123,27 +152,26 @@ __device__ __forceinline__ void scan_run(const Rec<T> *__restrict__ recs, uint32
     }
 }
 
-// Scan the cells [u0,u1] x [v0,v1] of `face`, skipping the already visited block [hu0,hu1] x [hv0,hv1] when
-// skip is set.  One row = one contiguous run of records (two table reads).
+// Scan the cells [u0,u1] x [v0,v1] of `face` (already clipped to the table), skipping the visited block
+// [hu0,hu1] x [hv0,hv1] when skip is set.  One row = one contiguous run of records (two table reads).
 template <typename T, int K>
-__device__ __forceinline__ void scan_rect(const IndexView<T> &ix, int face, int u0, int u1, int v0, int v1, bool skip,
-                                          int hu0, int hu1, int hv0, int hv1, T qx, T qy, T qz, T dub,
-                                          TopK<T, K> &top)
+__device__ __forceinline__ void scan_rect(const IndexView<T> &ix, int face, const CellRect &c, bool skip,
+                                          const CellRect &h, T qx, T qy, T qz, T dub, TopK<T, K> &top)
 {
-    const int G = ix.G;
-    for (int iv = v0; iv <= v1; ++iv) {
-        const uint32_t *row = ix.cell_start + ((size_t)face * G + iv) * G;
-        if (skip && iv >= hv0 && iv <= hv1) {
-            if (u0 < hu0) {
-                int e1 = min(u1, hu0 - 1);
-                scan_run<T, K>(ix.recs, __ldg(row + u0), __ldg(row + e1 + 1), qx, qy, qz, dub, top);
+    const FaceTable &ft = ix.fine;
+    const uint32_t *row = ix.cell_start + ft.base[face] + (int64_t)(c.v0 - ft.fv0[face]) * ft.fw[face] - ft.fu0[face];
+    for (int iv = c.v0; iv <= c.v1; ++iv, row += ft.fw[face]) {
+        if (skip && iv >= h.v0 && iv <= h.v1) {
+            if (c.u0 < h.u0) {
+                int e1 = min(c.u1, h.u0 - 1);
+                scan_run<T, K>(ix.recs, __ldg(row + c.u0), __ldg(row + e1 + 1), qx, qy, qz, dub, top);
             }
-            if (u1 > hu1) {
-                int s1 = max(u0, hu1 + 1);
-                scan_run<T, K>(ix.recs, __ldg(row + s1), __ldg(row + u1 + 1), qx, qy, qz, dub, top);
+            if (c.u1 > h.u1) {
+                int s1 = max(c.u0, h.u1 + 1);
+                scan_run<T, K>(ix.recs, __ldg(row + s1), __ldg(row + c.u1 + 1), qx, qy, qz, dub, top);
             }
         } else {
-            scan_run<T, K>(ix.recs, __ldg(row + u0), __ldg(row + u1 + 1), qx, qy, qz, dub, top);
+            scan_run<T, K>(ix.recs, __ldg(row + c.u0), __ldg(row + c.u1 + 1), qx, qy, qz, dub, top);
         }
     }
 }
@@ -158,58 +186,45 @@ __device__ void knn_search(const IndexView<T> &ix, T qx, T qy, T qz, T dub, TopK
     // ---- coarse emptiness test over the whole radius: most target pixels of a wide grid see no source at all
     const float s2r = cap_s2<T>(dub);
     const float sr = sqrtf(s2r);
-    {
-        uint32_t total = 0;
-        for (int f = 0; f < 6; ++f) {
-            CellRect c;
-            if (!face_rect(f, fx, fy, fz, s2r, sr, ix.Gc, c)) continue;
-            for (int iv = c.v0; iv <= c.v1; ++iv) {
-                const uint32_t *row = ix.coarse_start + ((size_t)f * ix.Gc + iv) * ix.Gc;
-                total += __ldg(row + c.u1 + 1) - __ldg(row + c.u0);
-            }
-        }
-        if (total == 0) return;
-    }
+    if (coarse_count(ix.coarse, ix.coarse_start, ix.Gc, fx, fy, fz, s2r, sr) == 0) return;
     // ---- phase A: grow a block of cells around the query's own cell until it holds k candidates
     int hface;
     float hu, hv;
     face_uv(fx, fy, fz, hface, hu, hv);
     const int cu = cell_coord(warp_uv(hu), G), cv = cell_coord(warp_uv(hv), G);
-    CellRect rr;  // everything within the radius on the home face
-    if (!face_rect(hface, fx, fy, fz, s2r, sr, G, rr)) {
-        rr.u0 = rr.u1 = cu;
-        rr.v0 = rr.v1 = cv;
-    }
-    int m = (K == 1) ? 0 : 1;
-    int hu0 = max(cu - m, rr.u0), hu1 = min(cu + m, rr.u1), hv0 = max(cv - m, rr.v0), hv1 = min(cv + m, rr.v1);
-    if (hu0 > hu1 || hv0 > hv1) {  // cannot happen (the home cell lies in its own cap) - stay safe
-        hu0 = hu1 = cu;
-        hv0 = hv1 = cv;
-        rr.u0 = min(rr.u0, cu);
-        rr.u1 = max(rr.u1, cu);
-        rr.v0 = min(rr.v0, cv);
-        rr.v1 = max(rr.v1, cv);
-    }
-    scan_rect<T, K>(ix, hface, hu0, hu1, hv0, hv1, false, 0, 0, 0, 0, qx, qy, qz, dub, top);
-    while (!top.full() && (hu0 > rr.u0 || hu1 < rr.u1 || hv0 > rr.v0 || hv1 < rr.v1)) {
-        m = 2 * m + 1;
-        int nu0 = max(cu - m, rr.u0), nu1 = min(cu + m, rr.u1), nv0 = max(cv - m, rr.v0), nv1 = min(cv + m, rr.v1);
-        scan_rect<T, K>(ix, hface, nu0, nu1, nv0, nv1, true, hu0, hu1, hv0, hv1, qx, qy, qz, dub, top);
-        hu0 = nu0;
-        hu1 = nu1;
-        hv0 = nv0;
-        hv1 = nv1;
+    CellRect hb;  // visited block on the home face (empty: u0 > u1)
+    hb.u0 = hb.v0 = 1;
+    hb.u1 = hb.v1 = 0;
+    CellRect rr;  // everything within the radius on the home face, clipped to the table
+    if (face_rect(hface, fx, fy, fz, s2r, sr, G, rr) && clip_rect(ix.fine, hface, rr)) {
+        int m = (K == 1) ? 0 : 1;
+        for (;;) {
+            CellRect nb;
+            nb.u0 = max(cu - m, rr.u0);
+            nb.u1 = min(cu + m, rr.u1);
+            nb.v0 = max(cv - m, rr.v0);
+            nb.v1 = min(cv + m, rr.v1);
+            if (nb.u0 <= nb.u1 && nb.v0 <= nb.v1) {
+                scan_rect<T, K>(ix, hface, nb, hb.u0 <= hb.u1, hb, qx, qy, qz, dub, top);
+                hb = nb;
+            }
+            if (top.full() || (nb.u0 == rr.u0 && nb.u1 == rr.u1 && nb.v0 == rr.v0 && nb.v1 == rr.v1)) break;
+            if (cu - m <= rr.u0 && cu + m >= rr.u1 && cv - m <= rr.v0 && cv + m >= rr.v1) break;
+            m = 2 * m + 1;
+        }
     }
     // ---- phase B: everything that can still beat (or tie) the current k-th distance, on every face
     T bound = top.full() ? top.d[K - 1] : dub;
     const float s2b = cap_s2<T>(bound);
     const float sb = sqrtf(s2b);
+#pragma unroll 1
     for (int f = 0; f < 6; ++f) {
         CellRect c;
         if (!face_rect(f, fx, fy, fz, s2b, sb, G, c)) continue;
-        bool home = (f == hface);
-        if (home && c.u0 >= hu0 && c.u1 <= hu1 && c.v0 >= hv0 && c.v1 <= hv1) continue;
-        scan_rect<T, K>(ix, f, c.u0, c.u1, c.v0, c.v1, home, hu0, hu1, hv0, hv1, qx, qy, qz, dub, top);
+        if (!clip_rect(ix.fine, f, c)) continue;
+        bool home = (f == hface) && (hb.u0 <= hb.u1);
+        if (home && c.u0 >= hb.u0 && c.u1 <= hb.u1 && c.v0 >= hb.v0 && c.v1 <= hb.v1) continue;
+        scan_rect<T, K>(ix, f, c, home, hb, qx, qy, qz, dub, top);
     }
 }
 

@@ -224,6 +224,9 @@ def _to_host(a):
 def _boundary_sides(geo_def):
     """Host copies of the four boundary sides (geometry.py:284-291), lon then lat."""
     if geometry.is_area(geo_def) and getattr(geo_def, "lons", None) is None:
+        cached = getattr(geo_def, "_prs_boundary_sides", None)
+        if cached is not None:  # an AreaDefinition is immutable: its boundary is computed once
+            return cached
         H, W = geo_def.height, geo_def.width
         slices = ((0, slice(None)), (slice(None), W - 1), (H - 1, slice(None, None, -1)), (slice(None, None, -1), 0))
         lons, lats = [], []
@@ -231,6 +234,10 @@ def _boundary_sides(geo_def):
             lo, la = _area_lonlats_device(geo_def, sl, geo_def.dtype)
             lons.append(lo.cpu().numpy().squeeze())
             lats.append(la.cpu().numpy().squeeze())
+        try:
+            geo_def._prs_boundary_sides = (lons, lats)
+        except AttributeError:  # pragma: no cover - foreign object without a __dict__
+            pass
         return lons, lats
     blons, blats = geo_def.get_boundary_lonlats()
     lons = [_to_host(s) for s in (blons.side1, blons.side2, blons.side3, blons.side4)]
@@ -293,14 +300,14 @@ def _reduce_box(boundary_geo_def, radius_of_influence):
     return box
 
 
-def _valid_mask_device(lon_t, lat_t, dtype, box, premask):
+def _valid_mask_device(lon_t, lat_t, dtype, box, premask, count=True):
     torch = _torch()
     n = lon_t.numel()
     valid = torch.empty(n, dtype=torch.uint8, device="cuda")
-    n_valid = ctypes.c_int64(0)
+    n_valid = ctypes.c_int64(-1)
     _cabi.check(_cabi.lib().prs_valid_mask(_ptr(lon_t), _ptr(lat_t), n, _tree_code(dtype),
                                            ctypes.byref(box) if box is not None else None, _ptr(premask), _ptr(valid),
-                                           ctypes.byref(n_valid), _stream()))
+                                           ctypes.byref(n_valid) if count else None, _stream()))
     return valid, n_valid.value
 
 
@@ -337,22 +344,22 @@ class _Source(object):
             if (geometry.is_coord(source_geo_def) or geometry.is_griddish(source_geo_def)) and \
                     geometry.is_griddish(target_geo_def):
                 box = _reduce_box(target_geo_def, radius_of_influence)
-        self.valid, self.n_valid = _valid_mask_device(lon_t, lat_t, self.dtype, box, premask)
+        # the number of valid points comes back with the index build (its single host round trip)
+        self.valid, _ = _valid_mask_device(lon_t, lat_t, self.dtype, box, premask, count=False)
         self.lon_t, self.lat_t = lon_t, lat_t
-        self.index = None
-        if self.n_valid > 0:
-            tdt = np.dtype(tree_dtype) if tree_dtype is not None else self.dtype
-            if tdt != self.dtype:
-                lon_t, lat_t = _dev(lon_t, tdt), _dev(lat_t, tdt)
-            handle = ctypes.c_void_p()
-            excl = _dev(exclude_mask).reshape(-1) if exclude_mask is not None else None
-            _cabi.check(_cabi.lib().prs_index_build(_ptr(lon_t), _ptr(lat_t), lon_t.numel(), _tree_code(tdt),
-                                                   _ptr(self.valid), _ptr(excl), _tree_code(tdt), int(neighbours),
-                                                   float(radius_of_influence), ctypes.byref(handle), _stream()))
-            self.index = _Index(handle, lon_t, lat_t)
-            self.tree_dtype = tdt
-        else:
-            self.tree_dtype = np.dtype(tree_dtype) if tree_dtype is not None else self.dtype
+        tdt = np.dtype(tree_dtype) if tree_dtype is not None else self.dtype
+        self.tree_dtype = tdt
+        if tdt != self.dtype:
+            lon_t, lat_t = _dev(lon_t, tdt), _dev(lat_t, tdt)
+        handle = ctypes.c_void_p()
+        excl = _dev(exclude_mask).reshape(-1) if exclude_mask is not None else None
+        _cabi.check(_cabi.lib().prs_index_build(_ptr(lon_t), _ptr(lat_t), lon_t.numel(), _tree_code(tdt),
+                                               _ptr(self.valid), _ptr(excl), _tree_code(tdt), int(neighbours),
+                                               float(radius_of_influence), ctypes.byref(handle), _stream()))
+        self.index = _Index(handle, lon_t, lat_t)
+        self.n_valid = int(self.index.n)
+        if self.n_valid == 0:  # EmptyResult of _create_resample_kdtree (kd_tree.py:480-481)
+            self.index = None
 
 
 def _make_target(source, target_geo_def, reduce_data, radius_of_influence, row0=0, nrows=None):
@@ -522,7 +529,8 @@ def _prepare_result(result, output_shape, is_masked_data, use_masked_fill_value,
     if use_masked_fill_value:
         result = np.ma.masked_equal(result, fill_value)
     if input_data_type is not None:
-        result = result.astype(input_data_type)
+        # the reference's astype copies; the array here is already a fresh buffer owned by the caller
+        result = result.astype(input_data_type, copy=False)
     return result
 
 

@@ -15,9 +15,9 @@ from .proj import prs_proj_params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC_DIR = os.path.join(_HERE, "csrc")
-_SO_PATH = os.path.join(_HERE, "libprs_b200.so")
-_SOURCES = ["prs_b200.cu"]
-_HEADERS = ["prs_common.cuh", "prs_scan.cuh", "prs_proj.cuh", "prs_index.cuh", "prs_query.cuh"]
+_SO_PATH = os.environ.get("PRS_B200_LIBRARY") or os.path.join(_HERE, "libprs_b200.so")  # override: kernel experiments
+_SOURCES = ["prs_b200.cu", "prs_query_inst.cu"]
+_HEADERS = ["prs_common.cuh", "prs_scan.cuh", "prs_proj.cuh", "prs_index.cuh", "prs_query.cuh", "prs_launch.cuh"]
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "prs_b200.h")
 
 PRS_F32, PRS_F64 = 0, 1
@@ -64,19 +64,41 @@ def needs_rebuild():
     return any(os.path.getmtime(d) > so_time for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """Compile the CUDA library for sm_100a into ``pyresample_b200/libprs_b200.so``."""
+_QUERY_INSTANCES = [(t, k) for t in ("float", "double") for k in (1, 4, 8, 16, 32)]
+
+
+def build(force=False, verbose=False, jobs=None):
+    """Compile the CUDA library for sm_100a into ``pyresample_b200/libprs_b200.so``.
+
+    ``prs_b200.cu`` holds the C-ABI and the small kernels; the query kernels are instantiated once per
+    (tree dtype, K) in ``prs_query_inst.cu`` - the translation units are compiled in parallel and linked.
+    """
     if not force and not needs_rebuild():
         return _SO_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
     if not any(os.path.exists(os.path.join(p, nvcc)) for p in os.environ.get("PATH", "").split(os.pathsep)) \
             and os.path.exists("/usr/local/cuda/bin/nvcc"):
         nvcc = "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", _SO_PATH + ".tmp"] + [os.path.join(_SRC_DIR, s) for s in _SOURCES]
+    obj_dir = os.path.join(_HERE, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+             "-Xcompiler", "-fPIC"] + os.environ.get("PRS_NVCC_FLAGS", "").split()
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd)
+        flags.append("-Xptxas=-v")
+    units = [(os.path.join(_SRC_DIR, "prs_b200.cu"), os.path.join(obj_dir, "prs_b200.o"), [])]
+    for t, k in _QUERY_INSTANCES:
+        units.append((os.path.join(_SRC_DIR, "prs_query_inst.cu"), os.path.join(obj_dir, "prs_query_%s_%d.o" % (t, k)),
+                      ["-DPRS_INST_T=%s" % t, "-DPRS_INST_K=%d" % k]))
+
+    def compile_unit(unit):
+        src, obj, defs = unit
+        subprocess.check_call([nvcc] + flags + defs + ["-c", src, "-o", obj])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=jobs or min(len(units), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(compile_unit, units))
+    subprocess.check_call([nvcc, "-shared", "-o", _SO_PATH + ".tmp"] + objs)
     os.replace(_SO_PATH + ".tmp", _SO_PATH)
     return _SO_PATH
 

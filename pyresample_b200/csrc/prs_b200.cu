@@ -97,7 +97,7 @@ __global__ void gather_nearest_kernel(const uint32_t *__restrict__ index, int64_
         uint32_t s = rank_to_source ? __ldg(rank_to_source + r) : r;
         src = (const char *)data + (size_t)s * row_bytes;
     }
-    copy_row((char *)out + (size_t)p * row_bytes, src, row_bytes, vec);
+    copy_row((char *)out + (size_t)p * row_bytes, src, (int)row_bytes, vec);
 }
 
 struct WeightedParams {
@@ -186,7 +186,7 @@ __global__ void compact_rows_kernel(const uint8_t *__restrict__ mask, const uint
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !mask[i]) return;
-    copy_row((char *)out + (size_t)pos[i] * row_bytes, (const char *)in + (size_t)i * row_bytes, row_bytes, vec);
+    copy_row((char *)out + (size_t)pos[i] * row_bytes, (const char *)in + (size_t)i * row_bytes, (int)row_bytes, vec);
 }
 
 __global__ void scatter_rows_kernel(const uint8_t *__restrict__ mask, const uint32_t *__restrict__ pos, int64_t n,
@@ -195,7 +195,7 @@ __global__ void scatter_rows_kernel(const uint8_t *__restrict__ mask, const uint
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const void *src = mask[i] ? (const void *)((const char *)in + (size_t)pos[i] * row_bytes) : fill_row;
-    copy_row((char *)out + (size_t)i * row_bytes, src, row_bytes, vec);
+    copy_row((char *)out + (size_t)i * row_bytes, src, (int)row_bytes, vec);
 }
 
 __global__ void rank_to_source_kernel(const uint8_t *__restrict__ valid, const uint32_t *__restrict__ pos, int64_t n,
@@ -222,24 +222,25 @@ struct TargetTables {
     uint8_t *col_ok = nullptr, *row_ok = nullptr;
 };
 
-template <typename T, int K> int launch_query_tk(const QueryParams &P, const IndexView<T> &ix, int tk, cudaStream_t st)
-{
-    unsigned grid = blocks_for(P.n_t);
-    if (grid == 0) return PRS_OK;
-    switch (tk) {
-    case PRS_TK_LONLAT:
-        query_kernel<T, K, PRS_TK_LONLAT><<<grid, TPB, 0, st>>>(P, ix);
-        break;
-    case PRS_TK_AREA_SEP:
-        query_kernel<T, K, PRS_TK_AREA_SEP><<<grid, TPB, 0, st>>>(P, ix);
-        break;
-    default:
-        query_kernel<T, K, PRS_TK_AREA_GEN><<<grid, TPB, 0, st>>>(P, ix);
-        break;
-    }
-    PRS_CKL();
-    return PRS_OK;
-}
+}  // namespace
+
+namespace prs {
+// defined in prs_query_inst.cu, one translation unit per (T, K)
+template <typename T, int K> int launch_query_tk(const QueryParams &P, const IndexView<T> &ix, int tk, cudaStream_t st);
+#define PRS_EXTERN_INST(T, K) extern template int launch_query_tk<T, K>(const QueryParams &, const IndexView<T> &, int, cudaStream_t);
+PRS_EXTERN_INST(float, 1)
+PRS_EXTERN_INST(float, 4)
+PRS_EXTERN_INST(float, 8)
+PRS_EXTERN_INST(float, 16)
+PRS_EXTERN_INST(float, 32)
+PRS_EXTERN_INST(double, 1)
+PRS_EXTERN_INST(double, 4)
+PRS_EXTERN_INST(double, 8)
+PRS_EXTERN_INST(double, 16)
+PRS_EXTERN_INST(double, 32)
+}  // namespace prs
+
+namespace {
 
 template <typename T> int launch_query_t(QueryParams &P, const prs_index *index, const prs_target *tg, cudaStream_t st)
 {
@@ -263,6 +264,9 @@ template <typename T> int launch_query_t(QueryParams &P, const prs_index *index,
         P.proj = tg->proj;
         P.grid = tg->grid;
         P.row0 = tg->row0;
+        if (tg->nrows > 0x7FFFFFF0LL || tg->grid.width > 0x7FFFFFF0LL) return fail(PRS_ENOSUP, "area too large");
+        P.nrows = (int)tg->nrows;
+        P.tiles_x = (int)((tg->grid.width + 31) / 32);
         bool separable = tg->proj.kind == PRS_PROJ_LONGLAT || tg->proj.kind == PRS_PROJ_EQC || tg->proj.kind == PRS_PROJ_MERC;
         if (separable && tg->n > 0) {
             tk = PRS_TK_AREA_SEP;
@@ -497,7 +501,8 @@ int prs_resample_nearest(const prs_index *index, const prs_target *target, doubl
     P.data = data;
     P.fill_row = fill_row;
     P.out = out;
-    P.row_bytes = row_bytes;
+    if (row_bytes > 0x7FFFFFF0LL) return fail(PRS_ENOSUP, "row too large");
+    P.row_bytes = (int)row_bytes;
     P.vec = pick_vec(row_bytes, data, fill_row, out);
     return launch_query(P, index, target, st);
 }

@@ -115,7 +115,7 @@ __global__ void build_xyz_kernel(const T *__restrict__ lon, const T *__restrict_
 }
 
 // Bounding rectangle (in probe cells) of the occupied probe cells of each face: rect[f] = {u0, v0, u1, v1}.
-__global__ void occ_rect_kernel(const uint8_t *__restrict__ occ, int *__restrict__ rect, uint32_t *__restrict__ n_occ)
+static __global__ void occ_rect_kernel(const uint8_t *__restrict__ occ, int *__restrict__ rect, uint32_t *__restrict__ n_occ)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 6 * OCC_G * OCC_G || !occ[i]) return;
@@ -169,7 +169,7 @@ __global__ void build_scatter_kernel(const Rec<T> *__restrict__ tmp, int64_t n_v
 }
 
 // Coarse table: number of points in each COARSE x COARSE block of fine cells, from the fine row prefix sums.
-__global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_start, const FaceTable fine, const FaceTable coarse,
+static __global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_start, const FaceTable fine, const FaceTable coarse,
                                     int64_t n_coarse, uint32_t *__restrict__ ctable)
 {
     int64_t cc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,11 +1,27 @@
 // Bounded exact k-NN against the cube-face cell index, with the sample gather / weighting fused into the
 // epilogue.  Replaces KDTree.query (kd_tree.py:545-548) + get_sample_from_neighbour_info (kd_tree.py:566-818).
+//
+// Work decomposition: the target is cut into tiles of 32 columns x QROWS rows.
+//   A. classify_kernel, one warp per tile: bound the tile's points by a spherical cap and ask the L2-resident
+//      coarse table whether ANY source point lies within (tile cap + radius).  Wide target grids are mostly far
+//      from the swath: such tiles get their final result (fill / sentinels) streamed out right away;
+//   B. query_kernel, one thread per point of the remaining tiles: grow a block of cells around the point's own
+//      cell until k candidates are found, then visit exactly the cells that can still beat the k-th distance;
+//   4. epilogue: neighbour info, or the gathered / weighted samples (nearest rows go through shared memory
+//      so that the warp writes contiguous 128-byte segments).
 #pragma once
 #include "prs_common.cuh"
 #include "prs_index.cuh"
 #include "prs_proj.cuh"
 
 namespace prs {
+
+constexpr int QROWS = 4;            // target rows per tile
+constexpr int QWARPS = 8;           // warps per block of the classification kernel
+constexpr int STAGE_ROW_BYTES = 64; // nearest rows up to this size are staged through shared memory
+#ifndef PRS_QUERY_MIN_BLOCKS
+#define PRS_QUERY_MIN_BLOCKS 3
+#endif
 
 // ------------------------------------------------------------------------------------------ top-k list
 // Sorted ascending by (d2, source index): ties go to the lowest source index (BASELINE north_star).
@@ -52,7 +68,6 @@ template <typename T> struct IndexView {
     uint32_t first_valid_source;
 };
 
-// Cell rectangle of one cube face that contains every point within the cap {p : |p - q|^2 <= bound}.
 struct CellRect {
     int u0, u1, v0, v1;
 };
@@ -68,12 +83,13 @@ __device__ __forceinline__ bool clip_rect(const FaceTable &t, int face, CellRect
     return r.u0 <= r.u1 && r.v0 <= r.v1;
 }
 
-// (fx, fy, fz): unit query vector.  s2: upper bound of sin^2 of the cap's angular radius.
-// Returns false when the cap cannot touch this face.  Closed form: the gnomonic image of a spherical cap is
-// a conic  w^T (q q^T - cos^2 I) w = 0,  w = (1, u, v);  its axis-aligned bounding box is
-//   u = (qa*qb -/+ s*sqrt(qa^2 + qb^2 - s^2)) / (qa^2 - s^2)      (same for v with qc).
-__device__ __forceinline__ bool face_rect(int face, float fx, float fy, float fz, float s2, float s, int G,
-                                          CellRect &r)
+// Gnomonic bounding box (u0, u1, v0, v1) on `face` of the cap around the unit vector (fx, fy, fz) whose angular
+// radius theta satisfies sin^2(theta) <= s2 (s = sqrt(s2)).  Returns false when the cap cannot touch the face.
+// Closed form: the gnomonic image of a spherical cap is the conic w^T (q q^T - cos^2 I) w = 0, w = (1, u, v), with
+//   u = (qa*qb -/+ s*sqrt(qa^2 + qb^2 - s^2)) / (qa^2 - s^2)      (same for v with qc),
+// qa the component along the face normal, qb / qc along the face's u / v axes.  Bounds carry float32 slack
+// (cell keys were computed from float32 coordinates, <= 1e-7 relative) and are NOT clamped to [-1, 1].
+__device__ __forceinline__ bool face_bounds(int face, float fx, float fy, float fz, float s2, float s, float b[4])
 {
     float qa, qb, qc;
     int axis = face >> 1;
@@ -91,31 +107,37 @@ __device__ __forceinline__ bool face_rect(int face, float fx, float fy, float fz
         qb = fx;
         qc = fy;
     }
-    // a point of the cap on this face has its dominant component >= 1/sqrt(3); the cap's angular radius
-    // is <= 1.2*s for s <= 0.8
+    // a point of the cap on this face has its dominant component >= 1/sqrt(3); theta <= 1.2*s for s <= 0.8
     if (qa < 0.57735f - 1.2f * s - 1e-3f) return false;
     float den = qa * qa - s2;
-    float u0 = -1.f, u1 = 1.f, v0 = -1.f, v1 = 1.f;
     if (den > 0.02f) {
         float inv = 1.0f / den;
         float ru = s * sqrtf(fmaxf(qa * qa + qb * qb - s2, 0.f));
         float rv = s * sqrtf(fmaxf(qa * qa + qc * qc - s2, 0.f));
-        u0 = (qa * qb - ru) * inv;
-        u1 = (qa * qb + ru) * inv;
-        v0 = (qa * qc - rv) * inv;
-        v1 = (qa * qc + rv) * inv;
-        // float32 slack: cell keys were computed from float32 coordinates (<= 1e-7 relative)
-        u0 -= 3e-6f * (1.0f + fabsf(u0));
-        u1 += 3e-6f * (1.0f + fabsf(u1));
-        v0 -= 3e-6f * (1.0f + fabsf(v0));
-        v1 += 3e-6f * (1.0f + fabsf(v1));
-        if (u1 < -1.f || u0 > 1.f || v1 < -1.f || v0 > 1.f) return false;
+        float u0 = (qa * qb - ru) * inv, u1 = (qa * qb + ru) * inv;
+        float v0 = (qa * qc - rv) * inv, v1 = (qa * qc + rv) * inv;
+        b[0] = u0 - 3e-6f * (1.0f + fabsf(u0));
+        b[1] = u1 + 3e-6f * (1.0f + fabsf(u1));
+        b[2] = v0 - 3e-6f * (1.0f + fabsf(v0));
+        b[3] = v1 + 3e-6f * (1.0f + fabsf(v1));
+        return !(b[1] < -1.f || b[0] > 1.f || b[3] < -1.f || b[2] > 1.f);
     }
-    r.u0 = cell_coord(warp_uv(u0) - 2e-6f, G);
-    r.u1 = cell_coord(warp_uv(u1) + 2e-6f, G);
-    r.v0 = cell_coord(warp_uv(v0) - 2e-6f, G);
-    r.v1 = cell_coord(warp_uv(v1) + 2e-6f, G);
+    b[0] = b[2] = -2.f;  // cap reaches the horizon of this chart: take the whole face
+    b[1] = b[3] = 2.f;
     return true;
+}
+__device__ __forceinline__ CellRect bounds_to_cells(const float b[4], int G)
+{
+    CellRect r;
+    r.u0 = cell_coord(warp_uv(b[0]) - 2e-6f, G);
+    r.u1 = cell_coord(warp_uv(b[1]) + 2e-6f, G);
+    r.v0 = cell_coord(warp_uv(b[2]) - 2e-6f, G);
+    r.v1 = cell_coord(warp_uv(b[3]) + 2e-6f, G);
+    return r;
+}
+__device__ __forceinline__ bool bounds_inside_face(const float b[4])
+{
+    return b[0] > -1.f && b[1] < 1.f && b[2] > -1.f && b[3] < 1.f;
 }
 
 // sin^2(theta) <= (d/R)^2 for chord d, inflated so that float32 rounding can never exclude a candidate
@@ -125,106 +147,165 @@ template <typename T> __device__ __forceinline__ float cap_s2(T d2)
     return (float)d2 * invR2 * 1.0002f + 1e-13f;
 }
 
-// Number of indexed points inside the cap's cell rectangles of the COARSE table (an upper bound of the number of
-// points within the cap; 0 proves there is none).
-__device__ __forceinline__ uint32_t coarse_count(const FaceTable &ct, const uint32_t *__restrict__ coarse_start, int Gc,
-                                                 float fx, float fy, float fz, float s2, float s)
+__device__ __forceinline__ int home_face(float fx, float fy, float fz)
 {
+    float ax = fabsf(fx), ay = fabsf(fy), az = fabsf(fz);
+    if (ax >= ay && ax >= az) return fx < 0.f ? 1 : 0;
+    if (ay >= az) return fy < 0.f ? 3 : 2;
+    return fz < 0.f ? 5 : 4;
+}
+
+__device__ __forceinline__ uint32_t coarse_rect_count(const FaceTable &ct, const uint32_t *__restrict__ coarse_start,
+                                                      int f, CellRect c)
+{
+    if (!clip_rect(ct, f, c)) return 0;
     uint32_t total = 0;
+    const uint32_t *row = coarse_start + ct.base[f] + (int64_t)(c.v0 - ct.fv0[f]) * ct.fw[f] - ct.fu0[f];
+    for (int iv = c.v0; iv <= c.v1; ++iv, row += ct.fw[f]) total += __ldg(row + c.u1 + 1) - __ldg(row + c.u0);
+    return total;
+}
+
+// Number of indexed points in the coarse cells touched by the cap: an upper bound of the points within the cap,
+// so 0 proves there is none.  hb / single: bounds on the home face and whether the cap stays on that face.
+__device__ __forceinline__ uint32_t coarse_count(const FaceTable &ct, const uint32_t *__restrict__ coarse_start, int Gc,
+                                                 float fx, float fy, float fz, float s2, float s, int hface,
+                                                 const float hb[4], bool single)
+{
+    uint32_t total = coarse_rect_count(ct, coarse_start, hface, bounds_to_cells(hb, Gc));
+    if (!single) {
 #pragma unroll 1
-    for (int f = 0; f < 6; ++f) {
-        CellRect c;
-        if (!face_rect(f, fx, fy, fz, s2, s, Gc, c)) continue;
-        if (!clip_rect(ct, f, c)) continue;
-        const uint32_t *row = coarse_start + ct.base[f] + (int64_t)(c.v0 - ct.fv0[f]) * ct.fw[f] - ct.fu0[f];
-        for (int iv = c.v0; iv <= c.v1; ++iv, row += ct.fw[f]) total += __ldg(row + c.u1 + 1) - __ldg(row + c.u0);
+        for (int f = 0; f < 6; ++f) {
+            float b[4];
+            if (f == hface || !face_bounds(f, fx, fy, fz, s2, s, b)) continue;
+            total += coarse_rect_count(ct, coarse_start, f, bounds_to_cells(b, Gc));
+        }
     }
     return total;
 }
 
+// Scan the cells of `face` in rectangle c (already clipped to the table), skipping the visited block h when
+// skip is set.  One row of cells = one contiguous run of records (two table reads); a row crossing the visited
+// block splits into at most two runs.
 template <typename T, int K>
-__device__ __forceinline__ void scan_run(const Rec<T> *__restrict__ recs, uint32_t s, uint32_t e, T qx, T qy, T qz,
-                                         T dub, TopK<T, K> &top)
-{
-    for (uint32_t i = s; i < e; ++i) {
-        Rec<T> r = load_rec(recs + i);
-        top.offer(dist2<T>(qx, qy, qz, r.x, r.y, r.z), r.idx, dub);
-    }
-}
-
-// Scan the cells [u0,u1] x [v0,v1] of `face` (already clipped to the table), skipping the visited block
-// [hu0,hu1] x [hv0,hv1] when skip is set.  One row = one contiguous run of records (two table reads).
-template <typename T, int K>
-__device__ __forceinline__ void scan_rect(const IndexView<T> &ix, int face, const CellRect &c, bool skip,
-                                          const CellRect &h, T qx, T qy, T qz, T dub, TopK<T, K> &top)
+__device__ __forceinline__ void scan_rect(const IndexView<T> &ix, int face, const CellRect c, bool skip, const CellRect h,
+                                          T qx, T qy, T qz, T dub, TopK<T, K> &top)
 {
     const FaceTable &ft = ix.fine;
     const uint32_t *row = ix.cell_start + ft.base[face] + (int64_t)(c.v0 - ft.fv0[face]) * ft.fw[face] - ft.fu0[face];
+#pragma unroll 1
     for (int iv = c.v0; iv <= c.v1; ++iv, row += ft.fw[face]) {
-        if (skip && iv >= h.v0 && iv <= h.v1) {
-            if (c.u0 < h.u0) {
-                int e1 = min(c.u1, h.u0 - 1);
-                scan_run<T, K>(ix.recs, __ldg(row + c.u0), __ldg(row + e1 + 1), qx, qy, qz, dub, top);
+        const bool split = skip && iv >= h.v0 && iv <= h.v1;
+#pragma unroll 1
+        for (int seg = 0; seg < 2; ++seg) {
+            int a, b;
+            if (!split) {
+                if (seg) break;
+                a = c.u0;
+                b = c.u1;
+            } else if (seg == 0) {
+                a = c.u0;
+                b = min(c.u1, h.u0 - 1);
+            } else {
+                a = max(c.u0, h.u1 + 1);
+                b = c.u1;
             }
-            if (c.u1 > h.u1) {
-                int s1 = max(c.u0, h.u1 + 1);
-                scan_run<T, K>(ix.recs, __ldg(row + s1), __ldg(row + c.u1 + 1), qx, qy, qz, dub, top);
+            if (a > b) continue;
+            const uint32_t s = __ldg(row + a), e = __ldg(row + b + 1);
+#pragma unroll 1
+            for (uint32_t i = s; i < e; ++i) {
+                Rec<T> r = load_rec(ix.recs + i);
+                top.offer(dist2<T>(qx, qy, qz, r.x, r.y, r.z), r.idx, dub);
             }
-        } else {
-            scan_run<T, K>(ix.recs, __ldg(row + c.u0), __ldg(row + c.u1 + 1), qx, qy, qz, dub, top);
         }
     }
 }
 
 // Exact bounded k-NN of one query point.  dub = (T)(radius^2); candidates need d2 < dub.
+//   phase 0: grow a block of cells around the query's own cell until it holds k candidates;
+//   phase 1: on the home face, visit every cell that can still beat (or tie) the k-th distance;
+//   phase 2: the same on the other faces the cap reaches (only near cube edges).
+// Written as one loop with a single scan site so that the top-k list stays in registers.
 template <typename T, int K>
-__device__ void knn_search(const IndexView<T> &ix, T qx, T qy, T qz, T dub, TopK<T, K> &top)
+__device__ __forceinline__ void knn_search(const IndexView<T> &ix, T qx, T qy, T qz, T dub, float s2r, float sr,
+                                           TopK<T, K> &top)
 {
     const float invR = (float)(1.0 / PRS_R);
     const float fx = (float)qx * invR, fy = (float)qy * invR, fz = (float)qz * invR;
     const int G = ix.G;
-    // ---- coarse emptiness test over the whole radius: most target pixels of a wide grid see no source at all
-    const float s2r = cap_s2<T>(dub);
-    const float sr = sqrtf(s2r);
-    if (coarse_count(ix.coarse, ix.coarse_start, ix.Gc, fx, fy, fz, s2r, sr) == 0) return;
-    // ---- phase A: grow a block of cells around the query's own cell until it holds k candidates
-    int hface;
-    float hu, hv;
-    face_uv(fx, fy, fz, hface, hu, hv);
-    const int cu = cell_coord(warp_uv(hu), G), cv = cell_coord(warp_uv(hv), G);
+    const int hface = home_face(fx, fy, fz);
+    float hbnd[4];
+    face_bounds(hface, fx, fy, fz, s2r, sr, hbnd);  // the home face always contains part of the cap
+    const bool single = bounds_inside_face(hbnd);
+    bool coarse_checked = false;
     CellRect hb;  // visited block on the home face (empty: u0 > u1)
     hb.u0 = hb.v0 = 1;
     hb.u1 = hb.v1 = 0;
-    CellRect rr;  // everything within the radius on the home face, clipped to the table
-    if (face_rect(hface, fx, fy, fz, s2r, sr, G, rr) && clip_rect(ix.fine, hface, rr)) {
-        int m = (K == 1) ? 0 : 1;
-        for (;;) {
-            CellRect nb;
-            nb.u0 = max(cu - m, rr.u0);
-            nb.u1 = min(cu + m, rr.u1);
-            nb.v0 = max(cv - m, rr.v0);
-            nb.v1 = min(cv + m, rr.v1);
-            if (nb.u0 <= nb.u1 && nb.v0 <= nb.v1) {
-                scan_rect<T, K>(ix, hface, nb, hb.u0 <= hb.u1, hb, qx, qy, qz, dub, top);
-                hb = nb;
-            }
-            if (top.full() || (nb.u0 == rr.u0 && nb.u1 == rr.u1 && nb.v0 == rr.v0 && nb.v1 == rr.v1)) break;
-            if (cu - m <= rr.u0 && cu + m >= rr.u1 && cv - m <= rr.v0 && cv + m >= rr.v1) break;
-            m = 2 * m + 1;
-        }
-    }
-    // ---- phase B: everything that can still beat (or tie) the current k-th distance, on every face
-    T bound = top.full() ? top.d[K - 1] : dub;
-    const float s2b = cap_s2<T>(bound);
-    const float sb = sqrtf(s2b);
+    CellRect rr = bounds_to_cells(hbnd, G);  // everything within the radius on the home face
+    int phase = clip_rect(ix.fine, hface, rr) ? 0 : 1;
+    if (phase == 1 && coarse_count(ix.coarse, ix.coarse_start, ix.Gc, fx, fy, fz, s2r, sr, hface, hbnd, single) == 0)
+        return;
+    int hf;
+    float hu, hv;
+    face_uv(fx, fy, fz, hf, hu, hv);
+    const int cu = cell_coord(warp_uv(hu), G), cv = cell_coord(warp_uv(hv), G);
+    int m = (K == 1) ? 0 : 1;
+    int f = 0;
+    float s2b = s2r, sb = sr;
 #pragma unroll 1
-    for (int f = 0; f < 6; ++f) {
+    for (;;) {
         CellRect c;
-        if (!face_rect(f, fx, fy, fz, s2b, sb, G, c)) continue;
-        if (!clip_rect(ix.fine, f, c)) continue;
-        bool home = (f == hface) && (hb.u0 <= hb.u1);
-        if (home && c.u0 >= hb.u0 && c.u1 <= hb.u1 && c.v0 >= hb.v0 && c.v1 <= hb.v1) continue;
-        scan_rect<T, K>(ix, f, c, home, hb, qx, qy, qz, dub, top);
+        c.u0 = c.v0 = 1;
+        c.u1 = c.v1 = 0;
+        int face = hface;
+        bool skip = false, scan = false;
+        if (phase == 0) {
+            c.u0 = max(cu - m, rr.u0);
+            c.u1 = min(cu + m, rr.u1);
+            c.v0 = max(cv - m, rr.v0);
+            c.v1 = min(cv + m, rr.v1);
+            scan = c.u0 <= c.u1 && c.v0 <= c.v1;
+            skip = hb.u0 <= hb.u1;
+        } else if (phase == 1) {
+            float b[4];
+            face_bounds(hface, fx, fy, fz, s2b, sb, b);
+            c = bounds_to_cells(b, G);
+            skip = hb.u0 <= hb.u1;
+            scan = clip_rect(ix.fine, hface, c) &&
+                   !(skip && c.u0 >= hb.u0 && c.u1 <= hb.u1 && c.v0 >= hb.v0 && c.v1 <= hb.v1);
+        } else {
+            float b[4];
+            face = f;
+            if (f != hface && face_bounds(f, fx, fy, fz, s2b, sb, b)) {
+                c = bounds_to_cells(b, G);
+                scan = clip_rect(ix.fine, f, c);
+            }
+        }
+        if (scan) scan_rect<T, K>(ix, face, c, skip, hb, qx, qy, qz, dub, top);
+        if (phase == 0) {
+            if (scan) hb = c;
+            if (top.full() || (cu - m <= rr.u0 && cu + m >= rr.u1 && cv - m <= rr.v0 && cv + m >= rr.v1)) {
+                phase = 1;
+                if (top.full()) {
+                    s2b = cap_s2<T>(top.d[K - 1]);
+                    sb = sqrtf(s2b);
+                }
+            } else {
+                // nothing (or too little) around the point itself: before widening the block, ask the coarse
+                // table whether there is any source point within the radius at all
+                if (!coarse_checked) {
+                    coarse_checked = true;
+                    if (top.id[0] == PRS_NONE &&
+                        coarse_count(ix.coarse, ix.coarse_start, ix.Gc, fx, fy, fz, s2r, sr, hface, hbnd, single) == 0)
+                        return;
+                }
+                m = 2 * m + 1;
+            }
+        } else if (phase == 1) {
+            if (single) break;
+            phase = 2;
+        } else {
+            if (++f >= 6) break;
+        }
     }
 }
 
@@ -252,6 +333,8 @@ struct QueryParams {
     prs_proj_params proj;
     prs_area_grid grid;
     int64_t row0;
+    int nrows;      // area targets: rows in this block
+    int tiles_x;    // tiles per tile-row
     const void *col_tab, *row_tab;
     const uint8_t *col_ok, *row_ok;
     // search
@@ -267,7 +350,7 @@ struct QueryParams {
     const void *data;
     const void *fill_row;
     void *out;
-    int64_t row_bytes;
+    int row_bytes;
     int vec;  // copy granularity in bytes (1, 2, 4, 8, 16)
     // gauss
     int channels;
@@ -279,35 +362,33 @@ struct QueryParams {
     void *stddev_out, *count_out;
 };
 
-__device__ __forceinline__ void copy_row(void *dst, const void *src, int64_t bytes, int vec)
+__device__ __forceinline__ void copy_row(void *dst, const void *src, int bytes, int vec)
 {
     switch (vec) {
     case 16:
-        for (int64_t o = 0; o < bytes; o += 16)
-            *reinterpret_cast<uint4 *>((char *)dst + o) = __ldg(reinterpret_cast<const uint4 *>((const char *)src + o));
+        for (int o = 0; o < bytes; o += 16)
+            *reinterpret_cast<uint4 *>((char *)dst + o) = *reinterpret_cast<const uint4 *>((const char *)src + o);
         break;
     case 8:
-        for (int64_t o = 0; o < bytes; o += 8)
-            *reinterpret_cast<uint2 *>((char *)dst + o) = __ldg(reinterpret_cast<const uint2 *>((const char *)src + o));
+        for (int o = 0; o < bytes; o += 8)
+            *reinterpret_cast<uint2 *>((char *)dst + o) = *reinterpret_cast<const uint2 *>((const char *)src + o);
         break;
     case 4:
-        for (int64_t o = 0; o < bytes; o += 4)
-            *reinterpret_cast<uint32_t *>((char *)dst + o) =
-                __ldg(reinterpret_cast<const uint32_t *>((const char *)src + o));
+        for (int o = 0; o < bytes; o += 4)
+            *reinterpret_cast<uint32_t *>((char *)dst + o) = *reinterpret_cast<const uint32_t *>((const char *)src + o);
         break;
     case 2:
-        for (int64_t o = 0; o < bytes; o += 2)
-            *reinterpret_cast<uint16_t *>((char *)dst + o) =
-                __ldg(reinterpret_cast<const uint16_t *>((const char *)src + o));
+        for (int o = 0; o < bytes; o += 2)
+            *reinterpret_cast<uint16_t *>((char *)dst + o) = *reinterpret_cast<const uint16_t *>((const char *)src + o);
         break;
     default:
-        for (int64_t o = 0; o < bytes; ++o) ((uint8_t *)dst)[o] = __ldg((const uint8_t *)src + o);
+        for (int o = 0; o < bytes; ++o) ((uint8_t *)dst)[o] = ((const uint8_t *)src)[o];
     }
 }
 
 // _resample_with_weights (kd_tree.py:741-818) + _calculate_uncertainty (kd_tree.py:821-859) for one target
-// point and one channel.  Tw: dtype the weight function is evaluated in (distance dtype);
-// Ta: accumulation / output dtype.  Neighbour i: source row src[i] (PRS_NONE = missing), weight w[i].
+// point and one channel.  Ta: accumulation / output dtype.  Neighbour i: source row src[i] (PRS_NONE = missing),
+// weight w[i].
 template <typename Ta, typename Td, int K>
 __device__ __forceinline__ void weighted_channel(const Td *__restrict__ data, int channels, int c, const uint32_t *src,
                                                  const Ta *w, int k, uint32_t first_valid_source, Ta fill, Ta &res_out,
@@ -357,8 +438,8 @@ __device__ __forceinline__ void weighted_channel(const Td *__restrict__ data, in
 }
 
 template <typename T, typename Ta, typename Td, int K>
-__device__ __forceinline__ void gauss_epilogue(const QueryParams &P, const IndexView<T> &ix, int64_t p,
-                                               const TopK<T, K> &top, bool valid)
+__device__ __noinline__ void gauss_epilogue(const QueryParams &P, const IndexView<T> &ix, int64_t p,
+                                            const TopK<T, K> &top, bool valid)
 {
     const int C = P.channels;
     const bool want_uncert = P.stddev_out != nullptr;
@@ -404,73 +485,129 @@ __device__ __forceinline__ void gauss_epilogue(const QueryParams &P, const Index
     }
 }
 
-template <typename T, int K, int TK>
-__global__ void __launch_bounds__(256) query_kernel(const __grid_constant__ QueryParams P, const IndexView<T> ix)
+__device__ __forceinline__ float warp_sum(float v)
 {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n_t) return;
-    // ---- target coordinates (kd_tree.py:513-534)
-    bool valid;
-    T qx = 0, qy = 0, qz = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------ tiles
+// A tile is 32 columns x QROWS rows of target points (arrays: 32*QROWS consecutive points, lane-strided).
+// tile_origin: first row / this lane's column of the tile (area targets); tile_point: raveled index or -1.
+__device__ __forceinline__ void tile_origin(const QueryParams &P, int TK, uint32_t tile, int lane, int &trow0, int &tcol)
+{
     if (TK == PRS_TK_LONLAT) {
-        T lon = ((const T *)P.tlon)[p], lat = ((const T *)P.tlat)[p];
-        valid = lonlat_in_range<T>(lon, lat);
-        if (valid) lonlat_to_xyz(lon, lat, qx, qy, qz);
-    } else if (TK == PRS_TK_AREA_SEP) {
-        const int64_t W = P.grid.width;
-        int64_t row = p / W, col = p - row * W;
-        valid = P.col_ok[col] && P.row_ok[row];
-        ColTab<T> ct = ((const ColTab<T> *)P.col_tab)[col];
-        RowTab<T> rt = ((const RowTab<T> *)P.row_tab)[row];
+        trow0 = tcol = 0;
+        return;
+    }
+    const uint32_t ty = tile / (uint32_t)P.tiles_x, tx = tile - ty * (uint32_t)P.tiles_x;
+    trow0 = (int)ty * QROWS;
+    tcol = (int)tx * 32 + lane;
+}
+__device__ __forceinline__ int64_t tile_point(const QueryParams &P, int TK, uint32_t tile, int trow0, int tcol, int j,
+                                              int lane)
+{
+    if (TK == PRS_TK_LONLAT) {
+        int64_t q = (int64_t)tile * (32 * QROWS) + j * 32 + lane;
+        return q < P.n_t ? q : -1;
+    }
+    const int W = (int)P.grid.width;
+    return (trow0 + j < P.nrows && tcol < W) ? (int64_t)(trow0 + j) * W + tcol : -1;
+}
+
+// Target coordinates of one point (kd_tree.py:513-534): validity + ECEF in the tree dtype.
+template <typename T, int TK>
+__device__ __forceinline__ bool target_point(const QueryParams &P, int64_t p, int trow, int tcol, T &qx, T &qy, T &qz)
+{
+    bool valid;
+    qx = qy = qz = 0;
+    if (TK == PRS_TK_AREA_SEP) {
+        ColTab<T> ct = ((const ColTab<T> *)P.col_tab)[tcol];
+        RowTab<T> rt = ((const RowTab<T> *)P.row_tab)[trow];
+        valid = P.col_ok[tcol] && P.row_ok[trow];
         qx = Ar<T>::mul(rt.rc, ct.c);
         qy = Ar<T>::mul(rt.rc, ct.s);
         qz = rt.rz;
     } else {
-        const int64_t W = P.grid.width;
-        int64_t row = p / W, col = p - row * W;
         T lon, lat;
-        area_pixel_lonlat<T>(P.proj, P.grid, P.row0 + row, col, lon, lat);
+        if (TK == PRS_TK_LONLAT) {
+            lon = ((const T *)P.tlon)[p];
+            lat = ((const T *)P.tlat)[p];
+        } else {
+            area_pixel_lonlat<T>(P.proj, P.grid, P.row0 + trow, tcol, lon, lat);
+        }
         valid = lonlat_in_range<T>(lon, lat);
         if (valid) lonlat_to_xyz(lon, lat, qx, qy, qz);
     }
     if (P.valid_extra) valid = valid && P.valid_extra[p];
-    // ---- search
-    TopK<T, K> top;
-    top.init();
-    const T dub = (T)(P.radius * P.radius);  // pykdtree: dtype(distance_upper_bound ** 2)
-    if (valid && ix.recs != nullptr) knn_search<T, K>(ix, qx, qy, qz, dub, top);
-    // ---- epilogue
+    return valid;
+}
+
+// Result of one target point (p < 0: lane has no point).  All 32 lanes of the warp call this together: nearest rows
+// are staged in shared memory and streamed out as contiguous 128-byte segments.
+template <typename T, int K, int TK>
+__device__ __forceinline__ void epilogue(const QueryParams &P, const IndexView<T> &ix, int64_t p, int trow, int tcol,
+                                         int lane, unsigned char *stage, const TopK<T, K> &top, bool valid)
+{
     if (P.mode == PRS_EPI_INFO) {
-        const int k = P.k;
-        uint32_t *io = P.idx_out + (size_t)p * k;
-        T *dout = P.dist_out ? (T *)P.dist_out + (size_t)p * k : nullptr;
+        bool kth = false;
+        if (p >= 0) {
+            const int k = P.k;
+            uint32_t *io = P.idx_out + (size_t)p * k;
+            T *dout = P.dist_out ? (T *)P.dist_out + (size_t)p * k : nullptr;
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-            if (i < k) {
-                uint32_t s = top.id[i];
-                uint32_t r = s == PRS_NONE ? ix.n_valid : (ix.rank ? __ldg(ix.rank + s) : s);
-                io[i] = r;
-                if (dout) dout[i] = s == PRS_NONE ? Ar<T>::inf() : Ar<T>::sqrt(top.d[i]);
+            for (int i = 0; i < K; ++i) {
+                if (i < k) {
+                    uint32_t s = top.id[i];
+                    io[i] = s == PRS_NONE ? ix.n_valid : (ix.rank ? __ldg(ix.rank + s) : s);
+                    if (dout) dout[i] = s == PRS_NONE ? Ar<T>::inf() : Ar<T>::sqrt(top.d[i]);
+                    if (i == k - 1 && s != PRS_NONE) kth = true;
+                }
             }
+            if (P.valid_out) P.valid_out[p] = valid ? 1 : 0;
         }
-        if (P.valid_out) P.valid_out[p] = valid ? 1 : 0;
         if (P.flags) {
-            bool kth = false;
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-                if (i == k - 1) kth = top.id[i] != PRS_NONE;
             if (kth && P.flags[0] == 0) P.flags[0] = 1;
-            if (!valid) atomicAdd(&P.flags[1], 1u);
+            unsigned bad = __ballot_sync(0xffffffffu, p >= 0 && !valid);
+            if (lane == 0 && bad) atomicAdd(&P.flags[1], (unsigned)__popc(bad));
         }
     } else if (P.mode == PRS_EPI_NEAREST) {
-        const void *src = top.id[0] == PRS_NONE ? P.fill_row : (const void *)((const char *)P.data + (size_t)top.id[0] * P.row_bytes);
-        copy_row((char *)P.out + (size_t)p * P.row_bytes, src, P.row_bytes, P.vec);
-    } else {
+        const void *src = top.id[0] == PRS_NONE ? P.fill_row
+                                                : (const void *)((const char *)P.data + (size_t)top.id[0] * P.row_bytes);
+        const bool staged = P.row_bytes <= STAGE_ROW_BYTES && TK != PRS_TK_LONLAT;
+        if (staged) {
+            const int rb = P.row_bytes;
+            if (p >= 0) copy_row(stage + lane * rb, src, rb, P.vec);
+            __syncwarp();
+            if (trow < P.nrows) {
+                const int W = (int)P.grid.width;
+                const int c0 = tcol - lane;
+                const int span = min(32, W - c0) * rb;
+                char *dst = (char *)P.out + ((size_t)trow * W + c0) * rb;
+                if ((rb & 3) == 0) {
+                    for (int o = lane * 4; o < span; o += 128)
+                        *reinterpret_cast<uint32_t *>(dst + o) = *reinterpret_cast<const uint32_t *>(stage + o);
+                } else {
+                    for (int o = lane; o < span; o += 32) dst[o] = stage[o];
+                }
+            }
+            __syncwarp();
+        } else if (p >= 0) {
+            copy_row((char *)P.out + (size_t)p * P.row_bytes, src, P.row_bytes, P.vec);
+        }
+    } else if (p >= 0) {
         if (P.flags) {
             bool kth = false;
 #pragma unroll
             for (int i = 0; i < K; ++i)
-                if (i == P.k - 1) kth = top.id[i] != PRS_NONE;
+                if (i == P.k - 1 && top.id[i] != PRS_NONE) kth = true;
             if (kth && P.flags[0] == 0) P.flags[0] = 1;
         }
         if (P.acc_f64) {
@@ -481,6 +618,133 @@ __global__ void __launch_bounds__(256) query_kernel(const __grid_constant__ Quer
         } else {
             gauss_epilogue<T, float, float, K>(P, ix, p, top, valid);
         }
+    }
+}
+
+// Kernel A: one warp per tile.  Bounds the tile's points by a spherical cap and asks the L2-resident coarse table
+// whether ANY source point lies within (cap + radius).  Tiles that see nothing get their final result right here
+// (fill value / "no neighbour" sentinels) - on wide target grids that is most of the output, written as a stream.
+// The other tiles are appended to live[] for kernel B.
+template <typename T, int K, int TK>
+__global__ void __launch_bounds__(QWARPS * 32, 4)
+    classify_kernel(const __grid_constant__ QueryParams P, const __grid_constant__ IndexView<T> ix, uint32_t n_tiles,
+                    uint32_t *__restrict__ live, uint32_t *__restrict__ n_live)
+{
+    __shared__ __align__(16) unsigned char stage_all[QWARPS][32 * STAGE_ROW_BYTES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * QWARPS + warp;
+    if (tile >= n_tiles) return;
+    int trow0, tcol;
+    tile_origin(P, TK, tile, lane, trow0, tcol);
+    const float invR = (float)(1.0 / PRS_R);
+    float ux[QROWS], uy[QROWS], uz[QROWS];
+    unsigned vmask = 0;
+    float sx = 0, sy = 0, sz = 0, cn = 0;
+#pragma unroll
+    for (int j = 0; j < QROWS; ++j) {
+        const int64_t p = tile_point(P, TK, tile, trow0, tcol, j, lane);
+        ux[j] = uy[j] = uz[j] = 0.f;
+        if (p >= 0) {
+            T qx, qy, qz;
+            if (target_point<T, TK>(P, p, trow0 + j, tcol, qx, qy, qz)) {
+                vmask |= 1u << j;
+                ux[j] = (float)qx * invR;
+                uy[j] = (float)qy * invR;
+                uz[j] = (float)qz * invR;
+                sx += ux[j];
+                sy += uy[j];
+                sz += uz[j];
+                cn += 1.f;
+            }
+        }
+    }
+    sx = warp_sum(sx);
+    sy = warp_sum(sy);
+    sz = warp_sum(sz);
+    cn = warp_sum(cn);
+    bool is_live = ix.recs != nullptr && cn > 0.f;
+    const float cnorm = sqrtf(sx * sx + sy * sy + sz * sz);
+    if (is_live && cnorm > 0.7f * cn) {  // points spread over < ~90 degrees: a meaningful cap exists
+        const float inv = 1.0f / cnorm;
+        const float cx = sx * inv, cy = sy * inv, cz = sz * inv;
+        float d2m = 0.f;
+#pragma unroll
+        for (int j = 0; j < QROWS; ++j)
+            if (vmask & (1u << j)) {
+                float dx = ux[j] - cx, dy = uy[j] - cy, dz = uz[j] - cz;
+                d2m = fmaxf(d2m, dx * dx + dy * dy + dz * dz);
+            }
+        d2m = warp_max(d2m);
+        const T dub = (T)(P.radius * P.radius);
+        const float sr = sqrtf(cap_s2<T>(dub));
+        // chord of the union cap on the unit sphere <= tile chord + radius chord (triangle inequality)
+        const float st = (sqrtf(d2m) * 1.0001f + 1e-6f) + sr;
+        const float s2t = st * st;
+        if (s2t < 0.25f) {
+            const int hf = home_face(cx, cy, cz);
+            float hb[4];
+            face_bounds(hf, cx, cy, cz, s2t, st, hb);
+            is_live = coarse_count(ix.coarse, ix.coarse_start, ix.Gc, cx, cy, cz, s2t, st, hf, hb,
+                                   bounds_inside_face(hb)) != 0;
+        }
+    }
+    if (is_live) {
+        if (lane == 0) live[atomicAdd(n_live, 1u)] = tile;
+        return;
+    }
+    unsigned char *stage = stage_all[warp];
+    if (P.mode == PRS_EPI_NEAREST && P.row_bytes <= STAGE_ROW_BYTES && (P.row_bytes & 3) == 0 && TK != PRS_TK_LONLAT) {
+        // fast path: the tile is rows of the fill pattern - stage 32 fill rows once, stream them out per tile row
+        const int rb = P.row_bytes;
+        copy_row(stage + lane * rb, P.fill_row, rb, P.vec);
+        __syncwarp();
+        const int W = (int)P.grid.width;
+        const int c0 = tcol - lane;
+        const int span = min(32, W - c0) * rb;
+#pragma unroll
+        for (int j = 0; j < QROWS; ++j) {
+            if (trow0 + j < P.nrows) {
+                char *dst = (char *)P.out + ((size_t)(trow0 + j) * W + c0) * rb;
+                for (int o = lane * 4; o < span; o += 128)
+                    *reinterpret_cast<uint32_t *>(dst + o) = *reinterpret_cast<const uint32_t *>(stage + o);
+            }
+        }
+        return;
+    }
+    TopK<T, K> top;
+    top.init();
+#pragma unroll 1
+    for (int j = 0; j < QROWS; ++j) {
+        const int64_t p = tile_point(P, TK, tile, trow0, tcol, j, lane);
+        epilogue<T, K, TK>(P, ix, p, trow0 + j, tcol, lane, stage, top, (vmask >> j) & 1u);
+    }
+}
+
+// Kernel B: the tiles that may have neighbours.  One block of QROWS warps per live tile, one point per thread.
+template <typename T, int K, int TK>
+__global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS)
+    query_kernel(const __grid_constant__ QueryParams P, const __grid_constant__ IndexView<T> ix,
+                 const uint32_t *__restrict__ live, const uint32_t *__restrict__ n_live)
+{
+    __shared__ __align__(16) unsigned char stage_all[QROWS][32 * STAGE_ROW_BYTES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t count = __ldg(n_live);
+    const T dub = (T)(P.radius * P.radius);  // pykdtree: dtype(distance_upper_bound ** 2)
+    const float s2r = cap_s2<T>(dub), sr = sqrtf(s2r);
+#pragma unroll 1
+    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) {
+        const uint32_t tile = __ldg(live + t);
+        int trow, tcol;
+        tile_origin(P, TK, tile, lane, trow, tcol);
+        const int64_t p = tile_point(P, TK, tile, trow, tcol, warp, lane);
+        trow += warp;
+        T qx = 0, qy = 0, qz = 0;
+        bool valid = false;
+        if (p >= 0) valid = target_point<T, TK>(P, p, trow, tcol, qx, qy, qz);
+        TopK<T, K> top;
+        top.init();
+        if (valid) knn_search<T, K>(ix, qx, qy, qz, dub, s2r, sr, top);
+        epilogue<T, K, TK>(P, ix, p, trow, tcol, lane, stage_all[warp], top, valid);
     }
 }
 

@@ -55,25 +55,33 @@ def all_gather_rows(local_block, height, group=None):
     return torch.cat([p[:n] for p, (_, n) in zip(parts, plan)], dim=0)
 
 
+def sharded_rows_apply(block_fn, height, group=None, gather=False):
+    """Run ``block_fn(row0, nrows) -> tensor (nrows, ...)`` for this rank's row block; optionally all-gather."""
+    import torch.distributed as dist
+    rank, world = 0, 1
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    row0, nrows = shard_rows(height, world, rank)
+    out = block_fn(row0, nrows)
+    if gather:
+        return all_gather_rows(out, height, group)
+    return out
+
+
 def resample_nearest_sharded(source_geo_def, data, target_geo_def, radius_of_influence, fill_value=0,
                              reduce_data=True, group=None, gather=False):
     """``kd_tree.resample_nearest`` for this rank's row block of ``target_geo_def`` (CUDA tensors in/out).
 
     Returns the local block ``(nrows, width[, C])`` or, with ``gather=True``, the full grid on every rank.
     """
-    import torch.distributed as dist
-
     from . import kd_tree
-    rank, world = 0, 1
-    if dist.is_available() and dist.is_initialized():
-        rank, world = dist.get_rank(group), dist.get_world_size(group)
     target = geometry.as_geo_def(target_geo_def)
-    row0, nrows = shard_rows(target.shape[0], world, rank)
-    out = kd_tree._resample(source_geo_def, data, target, 'nn', radius_of_influence, neighbours=1,
-                            fill_value=fill_value, reduce_data=reduce_data, _rows=(row0, nrows))
-    if gather:
-        return all_gather_rows(out, target.shape[0], group)
-    return out
+
+    def block(row0, nrows):
+        return kd_tree._resample(source_geo_def, data, target, 'nn', radius_of_influence, neighbours=1,
+                                 fill_value=fill_value, reduce_data=reduce_data, _rows=(row0, nrows))
+
+    return sharded_rows_apply(block, target.shape[0], group, gather)
 
 
 def concat_row_blocks(blocks):

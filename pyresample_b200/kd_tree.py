@@ -329,6 +329,7 @@ class _Source(object):
 
     def __init__(self, source_geo_def, target_geo_def, reduce_data, radius_of_influence, neighbours,
                  exclude_mask=None, tree_dtype=None):
+        _cabi.lib()  # fail loudly when the CUDA library or the GPU is missing: there is no CPU fallback
         source_geo_def = geometry.as_geo_def(source_geo_def)
         target_geo_def = geometry.as_geo_def(target_geo_def)
         self.geo_def = source_geo_def

@@ -345,6 +345,12 @@ class _Source(object):
             if (geometry.is_coord(source_geo_def) or geometry.is_griddish(source_geo_def)) and \
                     geometry.is_griddish(target_geo_def):
                 box = _reduce_box(target_geo_def, radius_of_influence)
+        # argument types (kd_tree.py:503-510); the reference checks them when it queries, i.e. after the
+        # reduce_data analysis above has already used the radius
+        if not isinstance(radius_of_influence, (int, float)):
+            raise TypeError('radius_of_influence must be number')
+        elif not isinstance(neighbours, int):
+            raise TypeError('neighbours must be integer')
         # the number of valid points comes back with the index build (its single host round trip)
         self.valid, _ = _valid_mask_device(lon_t, lat_t, self.dtype, box, premask, count=False)
         self.lon_t, self.lat_t = lon_t, lat_t

@@ -64,6 +64,11 @@ class BaseDefinition(object):
         lons, lats = self.lons, self.lats
         if lons is None or lats is None:
             raise ValueError('lon/lat values are not defined')
+        if hasattr(lons, "dims") and hasattr(lons, "data"):
+            # xarray DataArray: use the array underneath (pyresample/geometry.py:257-260)
+            lons, lats = lons.data, lats.data
+        if hasattr(lons, "compute"):  # dask arrays are materialised: the GPU path is eager
+            lons, lats = lons.compute(), lats.compute()
         if chunks is not None:
             raise NotImplementedError("dask chunking is not part of the B200 path; arrays are device tensors")
         if data_slice is not None:
@@ -101,6 +106,46 @@ class CoordinateDefinition(BaseDefinition):
         else:
             raise ValueError(('%s must be created with either '
                               'lon/lats of the same shape with same dtype') % self.__class__.__name__)
+
+    def geocentric_resolution(self, ellps='WGS84', radius=None, nadir_factor=2):
+        """Distance between the first two pixels of the middle row in geocentric metres
+        (pyresample/geometry.py:702-762).  Host-side, O(1)."""
+        if hasattr(self.lons, 'attrs') and self.lons.attrs.get('resolution') is not None:
+            return self.lons.attrs['resolution'] * nadir_factor
+        if self.ndim == 1:
+            raise RuntimeError("Can't confidently determine geocentric resolution for 1D swath.")
+        start_row = self.shape[0] // 2
+        lons = _to_numpy(self.lons[start_row: start_row + 1, :2]).ravel().astype(np.float64)
+        lats = _to_numpy(self.lats[start_row: start_row + 1, :2]).ravel().astype(np.float64)
+        xyz = _geodetic_to_geocentric(lons, lats, ellps, radius)
+        dist = np.linalg.norm(xyz[1] - xyz[0])
+        if not np.isfinite(dist):
+            raise RuntimeError("Could not calculate geocentric resolution")
+        return dist
+
+
+_GEOCENTRIC_ELLPS = {"WGS84": (6378137.0, 298.257223563), "GRS80": (6378137.0, 298.257222101)}
+
+
+def _to_numpy(a):
+    if hasattr(a, "detach"):
+        return a.detach().cpu().numpy()
+    if hasattr(a, "values") and not isinstance(a, np.ndarray):
+        return np.asarray(a.values)
+    return np.asarray(a)
+
+
+def _geodetic_to_geocentric(lons, lats, ellps='WGS84', radius=None):
+    """``+proj=cart`` on an ellipsoid (or a sphere of ``radius``), altitude 0 - used only for resolution estimates."""
+    if radius:
+        a, es = float(radius), 0.0
+    else:
+        a, rf = _GEOCENTRIC_ELLPS[ellps]
+        f = 1.0 / rf
+        es = 2 * f - f * f
+    lam, phi = np.deg2rad(lons), np.deg2rad(lats)
+    n = a / np.sqrt(1 - es * np.sin(phi) ** 2)
+    return np.stack((n * np.cos(phi) * np.cos(lam), n * np.cos(phi) * np.sin(lam), n * (1 - es) * np.sin(phi)), axis=1)
 
 
 class GridDefinition(CoordinateDefinition):
@@ -187,6 +232,29 @@ class AreaDefinition(BaseDefinition):
         if xs is not None:
             x = x[xs]
         return tuple(np.meshgrid(x, y))
+
+    def geocentric_resolution(self, ellps='WGS84', radius=None):
+        """Best estimate of the overall geocentric pixel size (pyresample/geometry.py:2691-2764): distances along
+        the middle row and middle column, mean of the first two of 10 histogram bin edges, maximum of both."""
+        def _safe_bin_edges(arr):
+            try:
+                return np.histogram_bin_edges(arr, bins=10)[:2]
+            except ValueError:
+                return arr[:2]
+        rows, cols = self.shape
+        hor_lon, hor_lat = self.get_lonlats(data_slice=(rows // 2, slice(None)), dtype=np.float64)
+        ver_lon, ver_lat = self.get_lonlats(data_slice=(slice(None), cols // 2), dtype=np.float64)
+        res = []
+        with np.errstate(invalid="ignore"):
+            for lo, la in ((hor_lon, hor_lat), (ver_lon, ver_lat)):
+                xyz = _geodetic_to_geocentric(np.asarray(lo).ravel(), np.asarray(la).ravel(), ellps, radius)
+                dist = np.linalg.norm(np.diff(xyz, axis=0), axis=1)
+                dist = dist[np.isfinite(dist)]
+                res.append(np.mean(_safe_bin_edges(dist)) if dist.size else 0)
+        out = max(res)
+        if not out:
+            raise RuntimeError("Could not calculate geocentric resolution")
+        return out
 
     def get_lonlats(self, nprocs=None, data_slice=None, cache=False, dtype=None, chunks=None):
         """Lon/lat of the pixel centres, inverse-projected on the GPU (pyresample/geometry.py:2558-2645)."""

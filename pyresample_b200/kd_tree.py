@@ -1065,3 +1065,7 @@ def resample_custom(source_geo_def, data, target_geo_def,
                      epsilon=epsilon, weight_funcs=weight_funcs,
                      fill_value=fill_value, reduce_data=reduce_data,
                      nprocs=nprocs, segments=segments, with_uncert=with_uncert)
+
+
+# the xarray API of this module (pyresample/kd_tree.py:902-1183) and the block kernels it imports at kd_tree.py:38
+from .xarray_nn import XArrayResamplerNN, _my_index, query_no_distance  # noqa: E402,F401

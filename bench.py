@@ -288,6 +288,9 @@ def main():
     clocks = sampler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
     q_all = [a.elapsed_time(b) for a, b in q_events]
+    if os.environ.get("PRS_BENCH_DEBUG"):
+        print("query ms per step:", " ".join("%.3f" % v for v in q_all), file=sys.stderr)
+        print("build ms per step:", " ".join("%.3f" % a.elapsed_time(b) for a, b in b_events), file=sys.stderr)
     b_all = [a.elapsed_time(b) for a, b in b_events]
     q_ms, b_ms = float(np.mean(q_all)), float(np.mean(b_all))
     if world > 1:

@@ -261,7 +261,9 @@ int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, c
         ix->Gc = 1;
         return PRS_OK;
     }
-    double lambda = k_hint > 4 ? (double)k_hint : 4.0;  // target points per cell
+    // target points per cell: the hot path of the query scans the 3x3 block around a point's cell (9*lambda
+    // candidates) and that block should hold the k nearest with room to spare
+    double lambda = k_hint > 4 ? 0.5 * (double)k_hint : 2.0;
     if (const char *env = getenv("PRS_CELL_OCCUPANCY")) {
         double v = atof(env);
         if (v > 0) lambda = v;

@@ -19,8 +19,10 @@ namespace prs {
 constexpr int QROWS = 4;            // target rows per tile
 constexpr int QWARPS = 8;           // warps per block of the classification kernel
 constexpr int STAGE_ROW_BYTES = 64; // nearest rows up to this size are staged through shared memory
+// Resident blocks per SM asked of the compiler for query_kernel (128 threads): the search is latency bound, so
+// k = 1 trades registers for occupancy (64 registers); larger top-k lists need the registers more.
 #ifndef PRS_QUERY_MIN_BLOCKS
-#define PRS_QUERY_MIN_BLOCKS 3
+#define PRS_QUERY_MIN_BLOCKS(K) ((K) <= 1 ? 8 : (K) <= 4 ? 6 : (K) <= 8 ? 4 : 3)
 #endif
 
 // ------------------------------------------------------------------------------------------ top-k list
@@ -40,6 +42,12 @@ template <typename T, int K> struct TopK {
     {
         if (!(d2 < dub)) return;  // strict radius test in the tree dtype (pykdtree)
         if (d2 < d[K - 1] || (d2 == d[K - 1] && idx < id[K - 1])) {
+            if (K > 1) {  // a cell may be visited twice (overlapping phases): never list a point twice
+                bool dup = false;
+#pragma unroll
+                for (int j = 0; j < K - 1; ++j) dup = dup || (id[j] == idx);
+                if (dup) return;
+            }
             d[K - 1] = d2;
             id[K - 1] = idx;
 #pragma unroll
@@ -220,37 +228,34 @@ __device__ __forceinline__ void scan_rect(const IndexView<T> &ix, int face, cons
     }
 }
 
-// Exact bounded k-NN of one query point.  dub = (T)(radius^2); candidates need d2 < dub.
-//   phase 0: grow a block of cells around the query's own cell until it holds k candidates;
+// General search: continues after the 3x3 block `hb` around the home cell (cu, cv) has been scanned.
+//   phase 0: grow the block (half-width m = 3, 7, ...) until it holds k candidates or covers the radius;
 //   phase 1: on the home face, visit every cell that can still beat (or tie) the k-th distance;
 //   phase 2: the same on the other faces the cap reaches (only near cube edges).
-// Written as one loop with a single scan site so that the top-k list stays in registers.
+// One loop with a single scan site.  This is the cold path (sparse data, swath edges, large k, cube edges).
 template <typename T, int K>
-__device__ __forceinline__ void knn_search(const IndexView<T> &ix, T qx, T qy, T qz, T dub, float s2r, float sr,
-                                           TopK<T, K> &top)
+__device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T qx, T qy, T qz, T dub, float s2r, float sr,
+                                                      TopK<T, K> top, CellRect hb, int hface, int cu, int cv)
 {
     const float invR = (float)(1.0 / PRS_R);
     const float fx = (float)qx * invR, fy = (float)qy * invR, fz = (float)qz * invR;
     const int G = ix.G;
-    const int hface = home_face(fx, fy, fz);
     float hbnd[4];
     face_bounds(hface, fx, fy, fz, s2r, sr, hbnd);  // the home face always contains part of the cap
     const bool single = bounds_inside_face(hbnd);
-    bool coarse_checked = false;
-    CellRect hb;  // visited block on the home face (empty: u0 > u1)
-    hb.u0 = hb.v0 = 1;
-    hb.u1 = hb.v1 = 0;
+    // too few candidates around the point itself: is there any source point within the radius at all?
+    if (top.id[0] == PRS_NONE &&
+        coarse_count(ix.coarse, ix.coarse_start, ix.Gc, fx, fy, fz, s2r, sr, hface, hbnd, single) == 0)
+        return top;
     CellRect rr = bounds_to_cells(hbnd, G);  // everything within the radius on the home face
-    int phase = clip_rect(ix.fine, hface, rr) ? 0 : 1;
-    if (phase == 1 && coarse_count(ix.coarse, ix.coarse_start, ix.Gc, fx, fy, fz, s2r, sr, hface, hbnd, single) == 0)
-        return;
-    int hf;
-    float hu, hv;
-    face_uv(fx, fy, fz, hf, hu, hv);
-    const int cu = cell_coord(warp_uv(hu), G), cv = cell_coord(warp_uv(hv), G);
-    int m = (K == 1) ? 0 : 1;
+    int phase = top.full() ? 1 : (clip_rect(ix.fine, hface, rr) ? 0 : 1);
+    int m = 3;
     int f = 0;
     float s2b = s2r, sb = sr;
+    if (top.full()) {
+        s2b = cap_s2<T>(top.d[K - 1]);
+        sb = sqrtf(s2b);
+    }
 #pragma unroll 1
     for (;;) {
         CellRect c;
@@ -282,7 +287,9 @@ __device__ __forceinline__ void knn_search(const IndexView<T> &ix, T qx, T qy, T
         }
         if (scan) scan_rect<T, K>(ix, face, c, skip, hb, qx, qy, qz, dub, top);
         if (phase == 0) {
-            if (scan) hb = c;
+            // the visited region is tracked as one rectangle; a block that does not contain the previous one is
+            // simply not recorded (its cells may be offered again later - TopK::offer drops duplicates)
+            if (scan && (hb.u0 > hb.u1 || (c.u0 <= hb.u0 && c.u1 >= hb.u1 && c.v0 <= hb.v0 && c.v1 >= hb.v1))) hb = c;
             if (top.full() || (cu - m <= rr.u0 && cu + m >= rr.u1 && cv - m <= rr.v0 && cv + m >= rr.v1)) {
                 phase = 1;
                 if (top.full()) {
@@ -290,14 +297,6 @@ __device__ __forceinline__ void knn_search(const IndexView<T> &ix, T qx, T qy, T
                     sb = sqrtf(s2b);
                 }
             } else {
-                // nothing (or too little) around the point itself: before widening the block, ask the coarse
-                // table whether there is any source point within the radius at all
-                if (!coarse_checked) {
-                    coarse_checked = true;
-                    if (top.id[0] == PRS_NONE &&
-                        coarse_count(ix.coarse, ix.coarse_start, ix.Gc, fx, fy, fz, s2r, sr, hface, hbnd, single) == 0)
-                        return;
-                }
                 m = 2 * m + 1;
             }
         } else if (phase == 1) {
@@ -307,6 +306,67 @@ __device__ __forceinline__ void knn_search(const IndexView<T> &ix, T qx, T qy, T
             if (++f >= 6) break;
         }
     }
+    return top;
+}
+
+// Exact bounded k-NN of one query point.  dub = (T)(radius^2); candidates need d2 < dub.
+// Hot path: scan the 3x3 block of cells around the point's own cell - three contiguous record runs, walked as ONE
+// flattened loop so that the lanes of a warp stay busy - then prove with the closed-form cap bounds that nothing
+// outside the block can beat or tie the k-th candidate.  Anything else goes to knn_search_general.
+template <typename T, int K>
+__device__ __forceinline__ void knn_search(const IndexView<T> &ix, T qx, T qy, T qz, T dub, float s2r, float sr,
+                                           TopK<T, K> &top)
+{
+    const float invR = (float)(1.0 / PRS_R);
+    const float fx = (float)qx * invR, fy = (float)qy * invR, fz = (float)qz * invR;
+    const int G = ix.G;
+    int hface;
+    float hu, hv;
+    face_uv(fx, fy, fz, hface, hu, hv);
+    const int cu = cell_coord(warp_uv(hu), G), cv = cell_coord(warp_uv(hv), G);
+    const FaceTable &ft = ix.fine;
+    CellRect hb;
+    hb.u0 = max(cu - 1, ft.fu0[hface]);
+    hb.u1 = min(cu + 1, ft.fu0[hface] + ft.fw[hface] - 1);
+    hb.v0 = max(cv - 1, ft.fv0[hface]);
+    hb.v1 = min(cv + 1, ft.fv0[hface] + ft.fh[hface] - 1);
+    if (hb.u0 <= hb.u1 && hb.v0 <= hb.v1) {
+        const int fw = ft.fw[hface];
+        const uint32_t *row = ix.cell_start + ft.base[hface] + (int64_t)(hb.v0 - ft.fv0[hface]) * fw - ft.fu0[hface];
+        const int nrows = hb.v1 - hb.v0 + 1;
+        // all run bounds first (independent loads in flight together), then one flattened candidate loop
+        uint32_t s0 = __ldg(row + hb.u0), e0 = __ldg(row + hb.u1 + 1);
+        uint32_t s1 = 0, e1 = 0, s2 = 0, e2 = 0;
+        if (nrows > 1) {
+            s1 = __ldg(row + fw + hb.u0);
+            e1 = __ldg(row + fw + hb.u1 + 1);
+        }
+        if (nrows > 2) {
+            s2 = __ldg(row + 2 * fw + hb.u0);
+            e2 = __ldg(row + 2 * fw + hb.u1 + 1);
+        }
+        const uint32_t n0 = e0 - s0, n01 = n0 + (e1 - s1), total = n01 + (e2 - s2);
+#pragma unroll 1
+        for (uint32_t t = 0; t < total; ++t) {
+            const uint32_t i = t < n0 ? s0 + t : (t < n01 ? s1 + (t - n0) : s2 + (t - n01));
+            Rec<T> r = load_rec(ix.recs + i);
+            top.offer(dist2<T>(qx, qy, qz, r.x, r.y, r.z), r.idx, dub);
+        }
+    } else {
+        hb.u0 = hb.v0 = 1;  // home block outside the table: nothing visited
+        hb.u1 = hb.v1 = 0;
+    }
+    if (top.full()) {
+        const float s2b = cap_s2<T>(top.d[K - 1]);
+        float b[4];
+        face_bounds(hface, fx, fy, fz, s2b, sqrtf(s2b), b);
+        if (bounds_inside_face(b)) {
+            CellRect c = bounds_to_cells(b, G);
+            // cells of the bound cap outside the table hold no points; inside the visited block nothing is left
+            if (!clip_rect(ft, hface, c) || (c.u0 >= hb.u0 && c.u1 <= hb.u1 && c.v0 >= hb.v0 && c.v1 <= hb.v1)) return;
+        }
+    }
+    top = knn_search_general<T, K>(ix, qx, qy, qz, dub, s2r, sr, top, hb, hface, cu, cv);
 }
 
 // ------------------------------------------------------------------------------------------ targets
@@ -722,7 +782,7 @@ __global__ void __launch_bounds__(QWARPS * 32, 4)
 
 // Kernel B: the tiles that may have neighbours.  One block of QROWS warps per live tile, one point per thread.
 template <typename T, int K, int TK>
-__global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS)
+__global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS(K))
     query_kernel(const __grid_constant__ QueryParams P, const __grid_constant__ IndexView<T> ix,
                  const uint32_t *__restrict__ live, const uint32_t *__restrict__ n_live)
 {

@@ -252,6 +252,23 @@ def _reduce_box(boundary_geo_def, radius_of_influence):
     kept in the boundary arrays' own dtype because the buffered limits are part of the bit-exact
     ``valid_input_index`` contract.
     """
+    is_cacheable = geometry.is_area(boundary_geo_def) and getattr(boundary_geo_def, "lons", None) is None
+    if is_cacheable:  # an AreaDefinition is immutable: its box depends on the radius only
+        cache = getattr(boundary_geo_def, "_prs_reduce_boxes", None)
+        if cache is not None and float(radius_of_influence) in cache:
+            return cache[float(radius_of_influence)]
+    box = _reduce_box_uncached(boundary_geo_def, radius_of_influence)
+    if is_cacheable:
+        try:
+            if getattr(boundary_geo_def, "_prs_reduce_boxes", None) is None:
+                boundary_geo_def._prs_reduce_boxes = {}
+            boundary_geo_def._prs_reduce_boxes[float(radius_of_influence)] = box
+        except AttributeError:  # pragma: no cover - foreign object without a __dict__
+            pass
+    return box
+
+
+def _reduce_box_uncached(boundary_geo_def, radius_of_influence):
     lon_sides, lat_sides = _boundary_sides(boundary_geo_def)
     box = prs_reduce_box()
     box.kind = PRS_REDUCE_ALL

@@ -200,7 +200,8 @@ def main():
     area = cfg["area"]
     H, W = area.shape
     channels = cfg["channels"]
-    row0, nrows = distributed.shard_rows(H, world, rank)
+    rows = distributed.cyclic_rows(H, world, rank)  # stripes of 64 rows dealt round-robin
+    nrows = rows[1]
 
     # ---- inputs: pinned host copies (e2e) and HBM-resident tensors (value); source broadcast once from rank 0
     host = {}
@@ -241,9 +242,10 @@ def main():
         """One pass of the hot path on resident inputs: masks + index build, then fused query + gather."""
         e0, e1, e2 = ev(), ev(), ev()
         e0.record()
-        source = kd_tree._Source(source_dev, area, True, radius, k)
+        source = kd_tree._Source(source_dev, area, True, radius, k, need_ranks=False,
+                                 cover_rows=rows if world > 1 else None)
         e1.record()
-        tg, n_t, keep = kd_tree._make_target(source, area, True, radius, row0, nrows)
+        tg, n_t, keep = kd_tree._make_target(source, area, True, radius, rows=rows)
         stream = kd_tree._stream()
         if mode == "nearest":
             out = torch.empty((n_t, channels), dtype=data_dev.dtype, device="cuda")
@@ -263,6 +265,7 @@ def main():
             b_events.append((e0, e1))
             q_events.append((e1, e2))
         info["n_valid"] = int(source.n_valid)
+        info["n_indexed"] = int(source.index.n_indexed)
         info["cells_per_side"] = int(source.index.cells_per_side)
         info["index_bytes"] = int(source.index.bytes)
         return out
@@ -331,7 +334,7 @@ def main():
             else:
                 blk = kd_tree._resample(src, dev["data"], area, 'custom', radius, neighbours=k,
                                         weight_funcs=[kd_tree._make_gauss(s) for s in sigmas] if channels > 1
-                                        else kd_tree._make_gauss(sigmas), _rows=(row0, nrows))
+                                        else kd_tree._make_gauss(sigmas), _rows=rows)
             return kd_tree._host(blk)
 
         import warnings
@@ -366,7 +369,8 @@ def main():
         peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         n_t_rank = nrows * W
         itemsize = data_dev.element_size()
-        b_alg = algorithmic_bytes(info["n_valid"], n_t_rank, channels, 4, itemsize)
+        # rank 0's share: the source points it indexes (all valid points at N = 1) and its target rows
+        b_alg = algorithmic_bytes(info["n_indexed"], n_t_rank, channels, 4, itemsize)
         achieved = b_alg / (q_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "prs::query_kernel (fused target transform + k-NN + gather)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -379,7 +383,9 @@ def main():
                 "config": {"workload": cfg["name"], "scale": args.scale, "source_points": int(n_src),
                            "valid_source_points": info["n_valid"], "target_pixels": int(n_t_total),
                            "channels": channels, "neighbours": k, "radius_m": radius,
-                           "sharding": "target rows, %d rank(s); source + index replicated" % world,
+                           "sharding": ("target rows in stripes of %d dealt round-robin over %d rank(s); source broadcast once "
+                                        "(NCCL), each rank indexes only the source points near its rows"
+                                        % (distributed.DEFAULT_STRIPE, world)),
                            "l2": "inputs (%.0f MB index + data, %.0f MB output) exceed the 126 MB L2; no flush needed"
                                  % ((info["index_bytes"] + data_dev.numel() * itemsize) / 1e6,
                                     n_t_total * channels * itemsize / 1e6),

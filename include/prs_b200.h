@@ -96,9 +96,16 @@ typedef struct prs_target {
     int64_t n;                /* number of target points (area: nrows * width) */
     prs_proj_params proj;     /* PRS_TARGET_AREA */
     prs_area_grid grid;
-    int64_t row0, nrows;      /* row block [row0, row0 + nrows) of the area: the multi-GPU / `segments` shard axis */
+    int64_t row0, nrows;      /* rows of the area owned by this call: the multi-GPU / `segments` shard axis.
+                                 Local row l is global row  row0 + (l / row_block) * row_stride + l % row_block ;
+                                 row_block == 0 means one contiguous block [row0, row0 + nrows). */
     const uint8_t *valid_extra; /* optional extra validity AND-ed in (grid -> swath reduce, kd_tree.py:438-451) */
+    int64_t row_block, row_stride; /* block-cyclic row ownership (rank r of N, stripes of B rows: row0 = r*B,
+                                      row_block = B, row_stride = N*B) */
 } prs_target;
+
+/* cells per cube-face side of the target coverage mask (prs_target_coverage / prs_index_build `cover`) */
+#define PRS_COVER_CELLS 512
 
 typedef struct prs_index prs_index; /* opaque spatial index over the valid source points */
 
@@ -135,7 +142,17 @@ int prs_valid_mask(const void *lon, const void *lat, int64_t n, int dtype, const
  * path always uses PRS_F64, kd_tree.py:979).  k_hint / radius_hint size the cells. */
 int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, const uint8_t *valid,
                     const uint8_t *exclude, int tree_dtype, int k_hint, double radius_hint,
-                    prs_index **index_out, void *stream);
+                    const uint8_t *cover, int flags, prs_index **index_out, void *stream);
+/* flags for prs_index_build */
+#define PRS_BUILD_RANKS 1 /* keep the rank table: needed by prs_query (index_array is in rank space) when some
+                             source points are invalid; the fused resample entry points do not need it */
+/* `cover` (optional, from prs_target_coverage): source points whose coverage cell is 0 cannot be within the
+ * radius of any target point of this rank and are left out of the index (they keep their rank). */
+
+/* Coverage mask of a target (one rank's rows) at PRS_COVER_CELLS^2 cells per cube face: cell = 1 when some
+ * target point may have a source point of that cell within `radius` (conservative, dilated by one cell).
+ * cover_out: uint8 [6 * PRS_COVER_CELLS^2], zeroed by the call. */
+int prs_target_coverage(const prs_target *target, double radius, uint8_t *cover_out, void *stream);
 int prs_index_destroy(prs_index *index);
 /* info[0]=n_source, [1]=n_valid (pykdtree .n), [2]=n_indexed, [3]=cells per cube-face side, [4]=bytes held,
  * [5]=tree dtype, [6]=coarse cells per side, [7]=1 if every source point is valid */

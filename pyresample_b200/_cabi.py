@@ -22,11 +22,13 @@ _INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "prs_b200.h")
 
 PRS_F32, PRS_F64 = 0, 1
 PRS_TARGET_LONLAT, PRS_TARGET_AREA = 0, 1
+PRS_BUILD_RANKS = 1
+PRS_COVER_CELLS = 512
 PRS_REDUCE_ALL, PRS_REDUCE_LAT_GE, PRS_REDUCE_LAT_LE, PRS_REDUCE_BOX, PRS_REDUCE_BOX_DATELINE = 0, 1, 2, 3, 4
 
 EXPORTED_SYMBOLS = (
     "prs_abi_version", "prs_last_error", "prs_launch_count", "prs_lonlat_to_xyz", "prs_area_lonlats", "prs_valid_mask",
-    "prs_index_build", "prs_index_destroy", "prs_index_info", "prs_query", "prs_resample_nearest",
+    "prs_index_build", "prs_target_coverage", "prs_index_destroy", "prs_index_info", "prs_query", "prs_resample_nearest",
     "prs_resample_gauss", "prs_gather_nearest", "prs_gather_weighted", "prs_compact_rows",
     "prs_rank_to_source", "prs_scatter_rows",
 )
@@ -49,7 +51,8 @@ class prs_target(ctypes.Structure):
                 ("lon", ctypes.c_void_p), ("lat", ctypes.c_void_p), ("n", ctypes.c_int64),
                 ("proj", prs_proj_params), ("grid", prs_area_grid),
                 ("row0", ctypes.c_int64), ("nrows", ctypes.c_int64),
-                ("valid_extra", ctypes.c_void_p)]
+                ("valid_extra", ctypes.c_void_p),
+                ("row_block", ctypes.c_int64), ("row_stride", ctypes.c_int64)]
 
 
 class PrsError(RuntimeError):
@@ -129,7 +132,8 @@ def load_library():
         L.prs_area_lonlats.argtypes = [ctypes.POINTER(prs_proj_params), ctypes.POINTER(prs_area_grid), i32,
                                        i64, i64, i64, i64, i64, i64, vp, vp, vp, vp]
         L.prs_valid_mask.argtypes = [vp, vp, i64, i32, ctypes.POINTER(prs_reduce_box), vp, vp, pi64, vp]
-        L.prs_index_build.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, dbl, ctypes.POINTER(vp), vp]
+        L.prs_index_build.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, dbl, vp, i32, ctypes.POINTER(vp), vp]
+        L.prs_target_coverage.argtypes = [ctypes.POINTER(prs_target), dbl, vp, vp]
         L.prs_index_destroy.argtypes = [vp]
         L.prs_index_info.argtypes = [vp, pi64]
         L.prs_query.argtypes = [vp, ctypes.POINTER(prs_target), i32, dbl, vp, vp, vp, pi64, vp]

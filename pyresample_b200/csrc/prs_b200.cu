@@ -8,6 +8,7 @@
 #include "prs_common.cuh"
 #include "prs_index.cuh"
 #include "prs_proj.cuh"
+#include "prs_launch.cuh"
 #include "prs_query.cuh"
 #include "prs_scan.cuh"
 
@@ -242,6 +243,60 @@ PRS_EXTERN_INST(double, 32)
 
 namespace {
 
+// Fill the target part of the kernel parameters; separable projections get their per-row / per-column tables.
+template <typename T> int setup_target(QueryParams &P, const prs_target *tg, int &tk, TargetTables &tabs, cudaStream_t st)
+{
+    tk = PRS_TK_LONLAT;
+    P.n_t = tg->n;
+    P.valid_extra = tg->valid_extra;
+    if (tg->kind == PRS_TARGET_AREA) {
+        if (tg->n != tg->nrows * tg->grid.width) return fail(PRS_EINVAL, "target.n != nrows * width");
+        P.proj = tg->proj;
+        P.grid = tg->grid;
+        P.row0 = tg->row0;
+        P.row_block = tg->row_block;
+        P.row_stride = tg->row_stride;
+        if (tg->nrows > 0x7FFFFFF0LL || tg->grid.width > 0x7FFFFFF0LL) return fail(PRS_ENOSUP, "area too large");
+        P.nrows = (int)tg->nrows;
+        P.tiles_x = (int)((tg->grid.width + 31) / 32);
+        bool separable = tg->proj.kind == PRS_PROJ_LONGLAT || tg->proj.kind == PRS_PROJ_EQC || tg->proj.kind == PRS_PROJ_MERC;
+        if (separable && tg->n > 0) {
+            tk = PRS_TK_AREA_SEP;
+            int64_t W = tg->grid.width, H = tg->nrows;
+            PRS_CK(cudaMallocAsync(&tabs.col_tab, sizeof(ColTab<T>) * (size_t)W, st));
+            PRS_CK(cudaMallocAsync(&tabs.row_tab, sizeof(RowTab<T>) * (size_t)H, st));
+            PRS_CK(cudaMallocAsync((void **)&tabs.col_ok, (size_t)W, st));
+            PRS_CK(cudaMallocAsync((void **)&tabs.row_ok, (size_t)H, st));
+            area_tables_kernel<T><<<blocks_for(W + H), TPB, 0, st>>>(tg->proj, tg->grid, tg->row0, tg->row_block,
+                                                                      tg->row_stride, H, (ColTab<T> *)tabs.col_tab,
+                                                                      tabs.col_ok, (RowTab<T> *)tabs.row_tab, tabs.row_ok);
+            PRS_CKL();
+            P.col_tab = tabs.col_tab;
+            P.row_tab = tabs.row_tab;
+            P.col_ok = tabs.col_ok;
+            P.row_ok = tabs.row_ok;
+        } else {
+            tk = PRS_TK_AREA_GEN;
+        }
+    } else {
+        P.tlon = tg->lon;
+        P.tlat = tg->lat;
+    }
+    return PRS_OK;
+}
+
+int free_tables(TargetTables &tabs, cudaStream_t st)
+{
+    if (tabs.col_tab) {
+        PRS_CK(cudaFreeAsync(tabs.col_tab, st));
+        PRS_CK(cudaFreeAsync(tabs.row_tab, st));
+        PRS_CK(cudaFreeAsync(tabs.col_ok, st));
+        PRS_CK(cudaFreeAsync(tabs.row_ok, st));
+        tabs.col_tab = nullptr;
+    }
+    return PRS_OK;
+}
+
 template <typename T> int launch_query_t(QueryParams &P, const prs_index *index, const prs_target *tg, cudaStream_t st)
 {
     IndexView<T> ix;
@@ -257,39 +312,8 @@ template <typename T> int launch_query_t(QueryParams &P, const prs_index *index,
     ix.first_valid_source = index->first_valid_source;
     int tk = PRS_TK_LONLAT;
     TargetTables tabs;
-    P.n_t = tg->n;
-    P.valid_extra = tg->valid_extra;
-    if (tg->kind == PRS_TARGET_AREA) {
-        if (tg->n != tg->nrows * tg->grid.width) return fail(PRS_EINVAL, "target.n != nrows * width");
-        P.proj = tg->proj;
-        P.grid = tg->grid;
-        P.row0 = tg->row0;
-        if (tg->nrows > 0x7FFFFFF0LL || tg->grid.width > 0x7FFFFFF0LL) return fail(PRS_ENOSUP, "area too large");
-        P.nrows = (int)tg->nrows;
-        P.tiles_x = (int)((tg->grid.width + 31) / 32);
-        bool separable = tg->proj.kind == PRS_PROJ_LONGLAT || tg->proj.kind == PRS_PROJ_EQC || tg->proj.kind == PRS_PROJ_MERC;
-        if (separable && tg->n > 0) {
-            tk = PRS_TK_AREA_SEP;
-            int64_t W = tg->grid.width, H = tg->nrows;
-            PRS_CK(cudaMallocAsync(&tabs.col_tab, sizeof(ColTab<T>) * (size_t)W, st));
-            PRS_CK(cudaMallocAsync(&tabs.row_tab, sizeof(RowTab<T>) * (size_t)H, st));
-            PRS_CK(cudaMallocAsync((void **)&tabs.col_ok, (size_t)W, st));
-            PRS_CK(cudaMallocAsync((void **)&tabs.row_ok, (size_t)H, st));
-            area_tables_kernel<T><<<blocks_for(W + H), TPB, 0, st>>>(tg->proj, tg->grid, tg->row0, H, (ColTab<T> *)tabs.col_tab,
-                                                                      tabs.col_ok, (RowTab<T> *)tabs.row_tab, tabs.row_ok);
-            PRS_CKL();
-            P.col_tab = tabs.col_tab;
-            P.row_tab = tabs.row_tab;
-            P.col_ok = tabs.col_ok;
-            P.row_ok = tabs.row_ok;
-        } else {
-            tk = PRS_TK_AREA_GEN;
-        }
-    } else {
-        P.tlon = tg->lon;
-        P.tlat = tg->lat;
-    }
-    int rc;
+    int rc = setup_target<T>(P, tg, tk, tabs, st);
+    if (rc != PRS_OK) return rc;
     int k = P.k;
     if (k <= 1)
         rc = launch_query_tk<T, 1>(P, ix, tk, st);
@@ -303,13 +327,8 @@ template <typename T> int launch_query_t(QueryParams &P, const prs_index *index,
         rc = launch_query_tk<T, 32>(P, ix, tk, st);
     else
         return fail(PRS_ENOSUP, "neighbours > 32 is not supported");
-    if (tabs.col_tab) {
-        PRS_CK(cudaFreeAsync(tabs.col_tab, st));
-        PRS_CK(cudaFreeAsync(tabs.row_tab, st));
-        PRS_CK(cudaFreeAsync(tabs.col_ok, st));
-        PRS_CK(cudaFreeAsync(tabs.row_ok, st));
-    }
-    return rc;
+    int rc2 = free_tables(tabs, st);
+    return rc != PRS_OK ? rc : rc2;
 }
 
 int launch_query(QueryParams &P, const prs_index *index, const prs_target *tg, cudaStream_t st)
@@ -412,7 +431,8 @@ int prs_valid_mask(const void *lon, const void *lat, int64_t n, int dtype, const
 }
 
 int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, const uint8_t *valid, const uint8_t *exclude,
-                    int tree_dtype, int k_hint, double radius_hint, prs_index **index_out, void *stream)
+                    int tree_dtype, int k_hint, double radius_hint, const uint8_t *cover, int flags,
+                    prs_index **index_out, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (!index_out) return fail(PRS_EINVAL, "index_out is null");
@@ -426,9 +446,11 @@ int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, cons
     ix->n_source = n;
     int rc;
     if (tree_dtype == PRS_F32)
-        rc = index_build_t<float>((const float *)lon, (const float *)lat, n, valid, exclude, k_hint, radius_hint, ix, st);
+        rc = index_build_t<float>((const float *)lon, (const float *)lat, n, valid, exclude, cover, flags, k_hint,
+                                  radius_hint, ix, st);
     else if (tree_dtype == PRS_F64)
-        rc = index_build_t<double>((const double *)lon, (const double *)lat, n, valid, exclude, k_hint, radius_hint, ix, st);
+        rc = index_build_t<double>((const double *)lon, (const double *)lat, n, valid, exclude, cover, flags, k_hint,
+                                   radius_hint, ix, st);
     else
         rc = fail(PRS_EINVAL, "tree_dtype must be PRS_F32 or PRS_F64");
     if (rc != PRS_OK) {
@@ -437,6 +459,27 @@ int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, cons
     }
     *index_out = ix;
     return PRS_OK;
+}
+
+int prs_target_coverage(const prs_target *target, double radius, uint8_t *cover_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!target || !cover_out) return fail(PRS_EINVAL, "null argument");
+    PRS_CK(cudaMemsetAsync(cover_out, 0, 6ull * PRS_COVER_CELLS * PRS_COVER_CELLS, st));
+    QueryParams P;
+    memset(&P, 0, sizeof(P));
+    P.radius = radius;
+    int tk = PRS_TK_LONLAT, rc;
+    TargetTables tabs;
+    if (target->dtype == PRS_F32) {
+        rc = setup_target<float>(P, target, tk, tabs, st);
+        if (rc == PRS_OK) rc = launch_coverage_t<float>(P, tk, cover_out, st);
+    } else {
+        rc = setup_target<double>(P, target, tk, tabs, st);
+        if (rc == PRS_OK) rc = launch_coverage_t<double>(P, tk, cover_out, st);
+    }
+    int rc2 = free_tables(tabs, st);
+    return rc != PRS_OK ? rc : rc2;
 }
 
 int prs_index_destroy(prs_index *ix)
@@ -478,6 +521,8 @@ int prs_query(const prs_index *index, const prs_target *target, int k, double ra
     P.dist_out = dist_out;
     P.valid_out = valid_out;
     if (!idx_out) return fail(PRS_EINVAL, "idx_out is null");
+    if (index && !index->all_valid && !index->rank && index->n_valid > 0)
+        return fail(PRS_EINVAL, "prs_query needs an index built with PRS_BUILD_RANKS (some source points are invalid)");
     if (flags_host) {
         PRS_CK(cudaMallocAsync((void **)&P.flags, 2 * sizeof(unsigned int), st));
         PRS_CK(cudaMemsetAsync(P.flags, 0, 2 * sizeof(unsigned int), st));

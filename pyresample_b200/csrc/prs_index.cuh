@@ -81,50 +81,90 @@ template <typename T> __device__ __forceinline__ void unit_f32(T x, T y, T z, fl
 }
 
 struct BuildCounters {
-    uint32_t n_valid;
-    uint32_t n_excluded;
-    uint32_t first_source;
-    uint32_t pad;
+    uint32_t n_valid;       // valid source points (pykdtree's .n)
+    uint32_t n_skipped;     // valid but excluded (query mask) or outside this rank's target coverage
+    uint32_t first_source;  // raveled index of the first valid point (rank 0)
+    uint32_t n_occ;         // occupied probe cells
 };
 
-// Pass 1: ECEF of every valid point, written in rank order; occupancy probe at OCC_G resolution.
+// Pass 1: ECEF of every valid point that this index needs; occupancy probe at OCC_G resolution.
+//   valid[i] == 0            -> not part of the tree at all
+//   exclude[i] (query mask)  -> keeps its rank, never returned
+//   cover (optional)         -> points whose coverage cell is 0 are beyond the radius of every target point of this
+//                               rank: skipped BEFORE the exact sin/cos (approximate intrinsics are enough because
+//                               the coverage mask is dilated by a whole cell)
 template <typename T>
 __global__ void build_xyz_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n,
                                  const uint8_t *__restrict__ valid, const uint8_t *__restrict__ exclude,
-                                 const uint32_t *__restrict__ rank, Rec<T> *__restrict__ tmp,
-                                 uint32_t *__restrict__ cellid, uint8_t *__restrict__ occ, BuildCounters *counters)
+                                 const uint8_t *__restrict__ cover, Rec<T> *__restrict__ tmp,
+                                 uint32_t *__restrict__ cellid, uint8_t *__restrict__ occ, BuildCounters *counters,
+                                 uint2 *__restrict__ block_counts)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !valid[i]) return;
-    uint32_t r = rank[i];
-    T x, y, z;
-    lonlat_to_xyz(lon[i], lat[i], x, y, z);
-    store_rec(tmp + r, x, y, z, (uint32_t)i);
-    if (r == 0) counters->first_source = (uint32_t)i;
-    bool skip = exclude && exclude[i];
-    cellid[r] = skip ? CELL_SKIP : 0u;
-    if (skip) {
-        atomicAdd(&counters->n_excluded, 1u);
-    } else {
-        float fx, fy, fz;
-        unit_f32<T>(x, y, z, fx, fy, fz);
-        int face, iu, iv;
-        face_cell_of(fx, fy, fz, OCC_G, face, iu, iv);
-        occ[(face * OCC_G + iv) * OCC_G + iu] = 1;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool v = i < n && valid[i];
+    bool skip = false;
+    if (v) {
+        skip = exclude && exclude[i];
+        const T lo = lon[i], la = lat[i];
+        if (!skip && cover) {
+            float slo, clo, sla, cla;
+            __sincosf((float)lo * 0.017453292f, &slo, &clo);
+            __sincosf((float)la * 0.017453292f, &sla, &cla);
+            int face, iu, iv;
+            face_cell_of(cla * clo, cla * slo, sla, PRS_COVER_CELLS, face, iu, iv);
+            skip = !cover[((size_t)face * PRS_COVER_CELLS + iv) * PRS_COVER_CELLS + iu];
+        }
+        if (!skip) {
+            T x, y, z;
+            lonlat_to_xyz(lo, la, x, y, z);
+            store_rec(tmp + i, x, y, z, (uint32_t)i);
+            float fx, fy, fz;
+            unit_f32<T>(x, y, z, fx, fy, fz);
+            int face, iu, iv;
+            face_cell_of(fx, fy, fz, OCC_G, face, iu, iv);
+            uint8_t *o = occ + (face * OCC_G + iv) * OCC_G + iu;
+            if (!*o) *o = 1;
+        }
+        // rank 0's source index: blocks run roughly in order, so almost all of them skip the atomic
+        if ((uint32_t)i < *(volatile uint32_t *)&counters->first_source) atomicMin(&counters->first_source, (uint32_t)i);
     }
+    if (i < n) cellid[i] = (v && !skip) ? 0u : CELL_SKIP;
+    const int nv = __syncthreads_count(v), ns = __syncthreads_count(v && skip);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = make_uint2((unsigned)nv, (unsigned)ns);
 }
 
-// Bounding rectangle (in probe cells) of the occupied probe cells of each face: rect[f] = {u0, v0, u1, v1}.
-static __global__ void occ_rect_kernel(const uint8_t *__restrict__ occ, int *__restrict__ rect, uint32_t *__restrict__ n_occ)
+// Reduce the per-block counts and the occupancy probe: number of valid / skipped points, bounding rectangle (in
+// probe cells) of the occupied probe cells of each face (rect[f] = {u0, v0, u1, v1}) and their number.
+static __global__ void build_reduce_kernel(const uint8_t *__restrict__ occ, const uint2 *__restrict__ block_counts,
+                                           int64_t n_blocks, int *__restrict__ rect, BuildCounters *counters)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 6 * OCC_G * OCC_G || !occ[i]) return;
-    int f = i / (OCC_G * OCC_G), iv = (i / OCC_G) % OCC_G, iu = i % OCC_G;
-    atomicMin(&rect[4 * f + 0], iu);
-    atomicMin(&rect[4 * f + 1], iv);
-    atomicMax(&rect[4 * f + 2], iu);
-    atomicMax(&rect[4 * f + 3], iv);
-    atomicAdd(n_occ, 1u);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    unsigned nv = 0, ns = 0, no = 0;
+    for (int64_t b = tid; b < n_blocks; b += nth) {
+        uint2 c = block_counts[b];
+        nv += c.x;
+        ns += c.y;
+    }
+    for (int i = tid; i < 6 * OCC_G * OCC_G; i += nth) {
+        if (!occ[i]) continue;
+        int f = i / (OCC_G * OCC_G), iv = (i / OCC_G) % OCC_G, iu = i % OCC_G;
+        atomicMin(&rect[4 * f + 0], iu);
+        atomicMin(&rect[4 * f + 1], iv);
+        atomicMax(&rect[4 * f + 2], iu);
+        atomicMax(&rect[4 * f + 3], iv);
+        ++no;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nv += __shfl_xor_sync(0xffffffffu, nv, o);
+        ns += __shfl_xor_sync(0xffffffffu, ns, o);
+        no += __shfl_xor_sync(0xffffffffu, no, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nv) atomicAdd(&counters->n_valid, nv);
+        if (ns) atomicAdd(&counters->n_skipped, ns);
+        if (no) atomicAdd(&counters->n_occ, no);
+    }
 }
 
 __device__ __forceinline__ int64_t table_key(const FaceTable &t, int face, int iu, int iv)
@@ -134,11 +174,11 @@ __device__ __forceinline__ int64_t table_key(const FaceTable &t, int face, int i
 
 // Pass 2: cell key of every indexed point + histogram into table[key + 1].
 template <typename T>
-__global__ void build_count_kernel(const Rec<T> *__restrict__ tmp, int64_t n_valid, int G, const FaceTable ft,
+__global__ void build_count_kernel(const Rec<T> *__restrict__ tmp, int64_t n, int G, const FaceTable ft,
                                    uint32_t *__restrict__ cellid, uint32_t *__restrict__ table)
 {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_valid) return;
+    if (j >= n) return;
     if (cellid[j] == CELL_SKIP) return;
     Rec<T> r = load_rec(tmp + j);
     float fx, fy, fz;
@@ -155,12 +195,11 @@ __global__ void build_count_kernel(const Rec<T> *__restrict__ tmp, int64_t n_val
 
 // Pass 3: scatter.  table[c + 1] holds start(c) after the exclusive scan and ends as start(c + 1).
 template <typename T>
-__global__ void build_scatter_kernel(const Rec<T> *__restrict__ tmp, int64_t n_valid,
-                                     const uint32_t *__restrict__ cellid, uint32_t *__restrict__ table,
-                                     Rec<T> *__restrict__ recs)
+__global__ void build_scatter_kernel(const Rec<T> *__restrict__ tmp, int64_t n, const uint32_t *__restrict__ cellid,
+                                     uint32_t *__restrict__ table, Rec<T> *__restrict__ recs)
 {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_valid) return;
+    if (j >= n) return;
     uint32_t c = cellid[j];
     if (c == CELL_SKIP) return;
     uint32_t pos = atomicAdd(&table[c + 1], 1u);
@@ -169,8 +208,8 @@ __global__ void build_scatter_kernel(const Rec<T> *__restrict__ tmp, int64_t n_v
 }
 
 // Coarse table: number of points in each COARSE x COARSE block of fine cells, from the fine row prefix sums.
-static __global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_start, const FaceTable fine, const FaceTable coarse,
-                                    int64_t n_coarse, uint32_t *__restrict__ ctable)
+static __global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_start, const FaceTable fine,
+                                           const FaceTable coarse, int64_t n_coarse, uint32_t *__restrict__ ctable)
 {
     int64_t cc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cc >= n_coarse) return;
@@ -190,68 +229,69 @@ static __global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_sta
 }
 
 template <typename T>
-int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, const uint8_t *exclude, int k_hint,
-                  double radius_hint, prs_index *ix, cudaStream_t st)
+int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, const uint8_t *exclude,
+                  const uint8_t *cover, int flags, int k_hint, double radius_hint, prs_index *ix, cudaStream_t st)
 {
     (void)radius_hint;
     const int TPB = 256;
     int rc = ensure_pool_configured();
     if (rc != PRS_OK) return rc;
     ix->stream = st;
-    // ranks of valid points (numpy's boolean compaction order)
-    uint32_t *rank = nullptr;
-    BuildCounters *counters = nullptr;
-    PRS_CK(cudaMallocAsync((void **)&rank, sizeof(uint32_t) * (size_t)n, st));
-    ix->rank = rank;
-    ix->bytes += sizeof(uint32_t) * (size_t)n;
+    const int64_t n_blocks = (n + TPB - 1) / TPB;
     const size_t occ_n = 6ull * OCC_G * OCC_G;
-    // scratch block: counters | n_occ | rect[24] | occ[occ_n]
+    // scratch block: counters | rect[24] | occ[occ_n] | block_counts[n_blocks]
     uint8_t *scratch = nullptr;
-    const size_t scratch_bytes = 256 + occ_n;
+    const size_t off_counts = (256 + occ_n + 15) & ~(size_t)15;
+    const size_t scratch_bytes = off_counts + sizeof(uint2) * (size_t)n_blocks;
     PRS_CK(cudaMallocAsync((void **)&scratch, scratch_bytes, st));
-    PRS_CK(cudaMemsetAsync(scratch, 0, scratch_bytes, st));
-    counters = (BuildCounters *)scratch;
-    uint32_t *n_occ_dev = (uint32_t *)(scratch + 16);
+    PRS_CK(cudaMemsetAsync(scratch, 0, off_counts, st));
+    BuildCounters *counters = (BuildCounters *)scratch;
     int *rect_dev = (int *)(scratch + 32);
     uint8_t *occ = scratch + 256;
+    uint2 *block_counts = (uint2 *)(scratch + off_counts);
     {
-        int init[24];
+        struct {
+            BuildCounters c;
+            uint32_t pad[4];
+            int rect[24];
+        } init;
+        memset(&init, 0, sizeof(init));
+        init.c.first_source = 0xFFFFFFFFu;
         for (int f = 0; f < 6; ++f) {
-            init[4 * f] = init[4 * f + 1] = 1 << 30;
-            init[4 * f + 2] = init[4 * f + 3] = -1;
+            init.rect[4 * f] = init.rect[4 * f + 1] = 1 << 30;
+            init.rect[4 * f + 2] = init.rect[4 * f + 3] = -1;
         }
-        PRS_CK(cudaMemcpyAsync(rect_dev, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        PRS_CK(cudaMemcpyAsync(scratch, &init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
-    rc = scan_u32<uint8_t>(valid, rank, n, 0, &counters->n_valid, st);
-    if (rc != PRS_OK) return rc;
-    // pass 1 (sized by the upper bound n so that no host round trip is needed first)
+    // pass 1 (records are addressed by source index, so no rank table is needed to build)
     Rec<T> *tmp = nullptr;
     uint32_t *cellid = nullptr;
     PRS_CK(cudaMallocAsync((void **)&tmp, sizeof(Rec<T>) * (size_t)n, st));
     PRS_CK(cudaMallocAsync((void **)&cellid, sizeof(uint32_t) * (size_t)n, st));
-    build_xyz_kernel<T><<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, st>>>(lon, lat, n, valid, exclude, rank, tmp, cellid,
-                                                                          occ, counters);
+    build_xyz_kernel<T><<<(unsigned)n_blocks, TPB, 0, st>>>(lon, lat, n, valid, exclude, cover, tmp, cellid, occ, counters,
+                                                            block_counts);
     PRS_CKL();
-    occ_rect_kernel<<<(unsigned)((occ_n + TPB - 1) / TPB), TPB, 0, st>>>(occ, rect_dev, n_occ_dev);
+    build_reduce_kernel<<<96, TPB, 0, st>>>(occ, block_counts, n_blocks, rect_dev, counters);
     PRS_CKL();
     // the one host round trip of the build: sizes the cell grid
     struct {
         BuildCounters c;
-        uint32_t n_occ;
-        uint32_t pad[3];
+        uint32_t pad[4];
         int rect[24];
     } h;
     PRS_CK(cudaMemcpyAsync(&h, scratch, sizeof(h), cudaMemcpyDeviceToHost, st));
     PRS_CK(cudaStreamSynchronize(st));
     PRS_CK(cudaFreeAsync(scratch, st));
     ix->n_valid = h.c.n_valid;
-    ix->n_indexed = (int64_t)h.c.n_valid - (int64_t)h.c.n_excluded;
-    ix->first_valid_source = h.c.first_source;
+    ix->n_indexed = (int64_t)h.c.n_valid - (int64_t)h.c.n_skipped;
+    ix->first_valid_source = h.c.first_source == 0xFFFFFFFFu ? 0u : h.c.first_source;
     ix->all_valid = (int64_t)h.c.n_valid == n;
-    if (ix->all_valid) {  // rank == source index: the table is not needed by queries
-        PRS_CK(cudaFreeAsync(rank, st));
-        ix->rank = nullptr;
-        ix->bytes -= sizeof(uint32_t) * (size_t)n;
+    if ((flags & PRS_BUILD_RANKS) && !ix->all_valid && ix->n_valid > 0) {
+        // rank of every source point among the valid ones = the index space of index_array (kd_tree.py:635)
+        PRS_CK(cudaMallocAsync((void **)&ix->rank, sizeof(uint32_t) * (size_t)n, st));
+        ix->bytes += sizeof(uint32_t) * (size_t)n;
+        rc = scan_u32<uint8_t>(valid, ix->rank, n, 0, nullptr, st);
+        if (rc != PRS_OK) return rc;
     }
     if (ix->n_indexed <= 0) {
         PRS_CK(cudaFreeAsync(tmp, st));
@@ -268,7 +308,7 @@ int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, c
         double v = atof(env);
         if (v > 0) lambda = v;
     }
-    uint32_t n_occ = h.n_occ ? h.n_occ : 1;
+    uint32_t n_occ = h.c.n_occ ? h.c.n_occ : 1;
     double g = (double)OCC_G * sqrt((double)ix->n_indexed / ((double)n_occ * lambda));
     int G = (int)ceil(g / COARSE) * COARSE;
     int Gmax = 16384;
@@ -317,22 +357,20 @@ int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, c
     PRS_CK(cudaMallocAsync((void **)&ix->cell_start, sizeof(uint32_t) * (size_t)(nf + 1), st));
     ix->bytes += sizeof(uint32_t) * (size_t)(nf + 1);
     PRS_CK(cudaMemsetAsync(ix->cell_start, 0, sizeof(uint32_t) * (size_t)(nf + 1), st));
-    unsigned gv = (unsigned)((ix->n_valid + TPB - 1) / TPB);
-    build_count_kernel<T><<<gv, TPB, 0, st>>>(tmp, ix->n_valid, G, ix->fine, cellid, ix->cell_start);
+    build_count_kernel<T><<<(unsigned)n_blocks, TPB, 0, st>>>(tmp, n, G, ix->fine, cellid, ix->cell_start);
     PRS_CKL();
     rc = scan_u32<uint32_t>(ix->cell_start + 1, ix->cell_start + 1, nf, 0, nullptr, st);
     if (rc != PRS_OK) return rc;
     size_t rec_bytes = sizeof(Rec<T>) * (size_t)ix->n_indexed;
     PRS_CK(cudaMallocAsync((void **)&ix->recs, rec_bytes, st));
     ix->bytes += rec_bytes;
-    build_scatter_kernel<T><<<gv, TPB, 0, st>>>(tmp, ix->n_valid, cellid, ix->cell_start, (Rec<T> *)ix->recs);
+    build_scatter_kernel<T><<<(unsigned)n_blocks, TPB, 0, st>>>(tmp, n, cellid, ix->cell_start, (Rec<T> *)ix->recs);
     PRS_CKL();
     // coarse table
     PRS_CK(cudaMallocAsync((void **)&ix->coarse_start, sizeof(uint32_t) * (size_t)(nc + 1), st));
     ix->bytes += sizeof(uint32_t) * (size_t)(nc + 1);
     PRS_CK(cudaMemsetAsync(ix->coarse_start, 0, sizeof(uint32_t), st));
-    FaceTable cb = ix->coarse;  // build_coarse_kernel reads base[f + 1]: keep a sentinel in a local copy
-    build_coarse_kernel<<<(unsigned)((nc + TPB - 1) / TPB), TPB, 0, st>>>(ix->cell_start, ix->fine, cb, nc,
+    build_coarse_kernel<<<(unsigned)((nc + TPB - 1) / TPB), TPB, 0, st>>>(ix->cell_start, ix->fine, ix->coarse, nc,
                                                                          ix->coarse_start);
     PRS_CKL();
     rc = scan_u32<uint32_t>(ix->coarse_start + 1, ix->coarse_start + 1, nc, 1, nullptr, st);

@@ -34,6 +34,26 @@ template <typename T, int K, int TK> inline int launch_query_k(const QueryParams
     return PRS_OK;
 }
 
+template <typename T, int TK> inline int launch_coverage_k(const QueryParams &P, uint8_t *cover, cudaStream_t st)
+{
+    if (P.n_t <= 0) return PRS_OK;
+    coverage_kernel<T, TK><<<(unsigned)((P.n_t + 255) / 256), 256, 0, st>>>(P, cover);
+    PRS_CKL();
+    return PRS_OK;
+}
+
+template <typename T> int launch_coverage_t(const QueryParams &P, int tk, uint8_t *cover, cudaStream_t st)
+{
+    switch (tk) {
+    case PRS_TK_LONLAT:
+        return launch_coverage_k<T, PRS_TK_LONLAT>(P, cover, st);
+    case PRS_TK_AREA_SEP:
+        return launch_coverage_k<T, PRS_TK_AREA_SEP>(P, cover, st);
+    default:
+        return launch_coverage_k<T, PRS_TK_AREA_GEN>(P, cover, st);
+    }
+}
+
 template <typename T, int K> int launch_query_tk(const QueryParams &P, const IndexView<T> &ix, int tk, cudaStream_t st)
 {
     switch (tk) {

@@ -393,7 +393,8 @@ struct QueryParams {
     prs_proj_params proj;
     prs_area_grid grid;
     int64_t row0;
-    int nrows;      // area targets: rows in this block
+    int64_t row_block, row_stride;  // block-cyclic row ownership (row_block == 0: contiguous)
+    int nrows;      // area targets: local rows of this call
     int tiles_x;    // tiles per tile-row
     const void *col_tab, *row_tab;
     const uint8_t *col_ok, *row_ok;
@@ -582,6 +583,14 @@ __device__ __forceinline__ int64_t tile_point(const QueryParams &P, int TK, uint
     return (trow0 + j < P.nrows && tcol < W) ? (int64_t)(trow0 + j) * W + tcol : -1;
 }
 
+// Global row of local row l (see prs_target in include/prs_b200.h).
+__device__ __forceinline__ int64_t global_row(int64_t row0, int64_t row_block, int64_t row_stride, int64_t l)
+{
+    if (row_block <= 0) return row0 + l;
+    const int64_t s = l / row_block;
+    return row0 + s * row_stride + (l - s * row_block);
+}
+
 // Target coordinates of one point (kd_tree.py:513-534): validity + ECEF in the tree dtype.
 template <typename T, int TK>
 __device__ __forceinline__ bool target_point(const QueryParams &P, int64_t p, int trow, int tcol, T &qx, T &qy, T &qz)
@@ -601,7 +610,7 @@ __device__ __forceinline__ bool target_point(const QueryParams &P, int64_t p, in
             lon = ((const T *)P.tlon)[p];
             lat = ((const T *)P.tlat)[p];
         } else {
-            area_pixel_lonlat<T>(P.proj, P.grid, P.row0 + trow, tcol, lon, lat);
+            area_pixel_lonlat<T>(P.proj, P.grid, global_row(P.row0, P.row_block, P.row_stride, trow), tcol, lon, lat);
         }
         valid = lonlat_in_range<T>(lon, lat);
         if (valid) lonlat_to_xyz(lon, lat, qx, qy, qz);
@@ -699,7 +708,6 @@ __global__ void __launch_bounds__(QWARPS * 32, 4)
     const float invR = (float)(1.0 / PRS_R);
     float ux[QROWS], uy[QROWS], uz[QROWS];
     unsigned vmask = 0;
-    float sx = 0, sy = 0, sz = 0, cn = 0;
 #pragma unroll
     for (int j = 0; j < QROWS; ++j) {
         const int64_t p = tile_point(P, TK, tile, trow0, tcol, j, lane);
@@ -711,22 +719,27 @@ __global__ void __launch_bounds__(QWARPS * 32, 4)
                 ux[j] = (float)qx * invR;
                 uy[j] = (float)qy * invR;
                 uz[j] = (float)qz * invR;
-                sx += ux[j];
-                sy += uy[j];
-                sz += uz[j];
-                cn += 1.f;
             }
         }
     }
-    sx = warp_sum(sx);
-    sy = warp_sum(sy);
-    sz = warp_sum(sz);
-    cn = warp_sum(cn);
-    bool is_live = ix.recs != nullptr && cn > 0.f;
-    const float cnorm = sqrtf(sx * sx + sy * sy + sz * sz);
-    if (is_live && cnorm > 0.7f * cn) {  // points spread over < ~90 degrees: a meaningful cap exists
-        const float inv = 1.0f / cnorm;
-        const float cx = sx * inv, cy = sy * inv, cz = sz * inv;
+    // cap centre: any valid point of the tile will do (the cap only has to contain the tile); take the first
+    // valid point of the lowest lane that has one
+    const unsigned has = __ballot_sync(0xffffffffu, vmask != 0);
+    bool is_live = ix.recs != nullptr && has != 0;
+    if (is_live) {
+        // prefer the point in the middle of the tile (smallest cap), else the first valid one
+        const int src_lane = (has & (1u << 16)) ? 16 : __ffs(has) - 1;
+        const int jj = (vmask & (1u << (QROWS / 2))) ? QROWS / 2 : __ffs(vmask) - 1;  // used on lanes with a point
+        float mx = 0.f, my = 0.f, mz = 0.f;
+#pragma unroll
+        for (int j = 0; j < QROWS; ++j)
+            if (j == jj) {
+                mx = ux[j];
+                my = uy[j];
+                mz = uz[j];
+            }
+        const float cx = __shfl_sync(0xffffffffu, mx, src_lane), cy = __shfl_sync(0xffffffffu, my, src_lane),
+                    cz = __shfl_sync(0xffffffffu, mz, src_lane);
         float d2m = 0.f;
 #pragma unroll
         for (int j = 0; j < QROWS; ++j)
@@ -761,10 +774,29 @@ __global__ void __launch_bounds__(QWARPS * 32, 4)
         const int W = (int)P.grid.width;
         const int c0 = tcol - lane;
         const int span = min(32, W - c0) * rb;
+        char *dst0 = (char *)P.out + ((size_t)trow0 * W + c0) * rb;
+        const size_t row_pitch = (size_t)W * rb;
+        if (((reinterpret_cast<uintptr_t>(dst0) | row_pitch | (size_t)span) & 15) == 0) {
+            // 16-byte stores: each lane keeps its (at most STAGE_ROW_BYTES / 16) pieces of the pattern in registers
+            uint4 v[STAGE_ROW_BYTES / 16];
+#pragma unroll
+            for (int i = 0; i < STAGE_ROW_BYTES / 16; ++i)
+                if (lane * 16 + i * 512 < span) v[i] = *reinterpret_cast<const uint4 *>(stage + lane * 16 + i * 512);
+#pragma unroll
+            for (int j = 0; j < QROWS; ++j) {
+                if (trow0 + j < P.nrows) {
+                    char *dst = dst0 + j * row_pitch;
+#pragma unroll
+                    for (int i = 0; i < STAGE_ROW_BYTES / 16; ++i)
+                        if (lane * 16 + i * 512 < span) *reinterpret_cast<uint4 *>(dst + lane * 16 + i * 512) = v[i];
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < QROWS; ++j) {
             if (trow0 + j < P.nrows) {
-                char *dst = (char *)P.out + ((size_t)(trow0 + j) * W + c0) * rb;
+                char *dst = dst0 + j * row_pitch;
                 for (int o = lane * 4; o < span; o += 128)
                     *reinterpret_cast<uint32_t *>(dst + o) = *reinterpret_cast<const uint32_t *>(stage + o);
             }
@@ -808,11 +840,49 @@ __global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS(K))
     }
 }
 
+// Coverage of a target at PRS_COVER_CELLS^2 cells per cube face: marks every cell that the cap (point, radius)
+// touches, dilated by one cell, so that the index build of this rank may drop source points elsewhere.
+template <typename T, int TK>
+__global__ void coverage_kernel(const __grid_constant__ QueryParams P, uint8_t *__restrict__ cover)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_t) return;
+    int trow = 0, tcol = 0;
+    if (TK != PRS_TK_LONLAT) {
+        const int64_t W = P.grid.width;
+        trow = (int)(p / W);
+        tcol = (int)(p - (int64_t)trow * W);
+    }
+    T qx, qy, qz;
+    if (!target_point<T, TK>(P, p, trow, tcol, qx, qy, qz)) return;
+    const float invR = (float)(1.0 / PRS_R);
+    const float fx = (float)qx * invR, fy = (float)qy * invR, fz = (float)qz * invR;
+    const T dub = (T)(P.radius * P.radius);
+    const float s2 = cap_s2<T>(dub), s = sqrtf(s2);
+    const int CG = PRS_COVER_CELLS;
+#pragma unroll 1
+    for (int f = 0; f < 6; ++f) {
+        float b[4];
+        if (!face_bounds(f, fx, fy, fz, s2, s, b)) continue;
+        CellRect c = bounds_to_cells(b, CG);
+        c.u0 = max(c.u0 - 1, 0);
+        c.v0 = max(c.v0 - 1, 0);
+        c.u1 = min(c.u1 + 1, CG - 1);
+        c.v1 = min(c.v1 + 1, CG - 1);
+        for (int iv = c.v0; iv <= c.v1; ++iv)
+            for (int iu = c.u0; iu <= c.u1; ++iu) {
+                uint8_t *cell = cover + ((size_t)f * CG + iv) * CG + iu;
+                if (!*cell) *cell = 1;
+            }
+    }
+}
+
 // Per-row / per-column tables of a separable projection (longlat, eqc, merc): lon depends on the column
 // only and lat on the row only, so the per-pixel transform collapses to two multiplies.
 template <typename T>
-__global__ void area_tables_kernel(const prs_proj_params P, const prs_area_grid g, int64_t row0, int64_t nrows,
-                                   ColTab<T> *col_tab, uint8_t *col_ok, RowTab<T> *row_tab, uint8_t *row_ok)
+__global__ void area_tables_kernel(const prs_proj_params P, const prs_area_grid g, int64_t row0, int64_t row_block,
+                                   int64_t row_stride, int64_t nrows, ColTab<T> *col_tab, uint8_t *col_ok,
+                                   RowTab<T> *row_tab, uint8_t *row_ok)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const T NaN = Ar<T>::nan();
@@ -840,7 +910,7 @@ __global__ void area_tables_kernel(const prs_proj_params P, const prs_area_grid 
     } else if (i < g.width + nrows) {
         int64_t r = i - g.width;
         T lon, lat;
-        area_pixel_lonlat<T>(P, g, row0 + r, 0, lon, lat);
+        area_pixel_lonlat<T>(P, g, global_row(row0, row_block, row_stride, r), 0, lon, lat);
         bool ok = (lat <= (T)90) && (lat >= (T)-90);
         T rc = NaN, rz = NaN;
         if (ok) {

@@ -1,18 +1,26 @@
 """Multi-GPU execution of the kd-tree resampling path: one process per GPU, target rows sharded.
 
 The reference already processes the target in independent row blocks (``segments``,
-pyresample/kd_tree.py:343-366 via geometry._get_slice, geometry.py:3052-3068); that is the shard axis here.
-Rank ``r`` of ``world`` owns rows ``_get_slice(world, shape)[r]`` of the target, generates the coordinates of
-those rows itself (no input traffic) and needs no exchange with other ranks during the query.  The source
-swath (lon, lat, data) is broadcast once from rank 0 with ``torch.distributed`` (NCCL over NVLink on GPUs,
-gloo in the CPU tests); every rank then builds the same deterministic index.  An optional all-gather
-assembles the full grid on every rank.
+pyresample/kd_tree.py:343-366 via geometry._get_slice, geometry.py:3052-3068); rows are the shard axis here too.
+
+* **Row ownership.**  ``shard_rows`` gives rank ``r`` the contiguous block ``_get_slice(world, shape)[r]``
+  (the reference's segment arithmetic).  ``cyclic_rows`` deals stripes of ``stripe`` rows round-robin
+  (rank r owns global rows g with ``(g // stripe) % world == r``): a swath usually covers only part of a
+  grid, and stripes give every rank the same share of the covered rows.  Either way a rank generates the
+  coordinates of its rows itself from the *global* pixel generator (global row index, identical rounding).
+* **Source.**  Broadcast once from rank 0 (``torch.distributed``: NCCL over NVLink on GPUs, gloo in the CPU
+  tests).  Every rank then indexes only the source points that can be within the radius of one of ITS rows
+  (coverage mask, ``prs_target_coverage`` -> ``cover`` of ``prs_index_build``): index build and query both shrink
+  with the number of ranks, and no rank exchanges anything during the query.
+* **Result.**  Each rank holds its rows; ``all_gather_rows`` / ``assemble_rows`` put the grid back together.
 """
 from __future__ import annotations
 
 import numpy as np
 
 from . import geometry
+
+DEFAULT_STRIPE = 64  # rows per stripe of the block-cyclic distribution (a multiple of the 4-row query tiles)
 
 
 def shard_rows(height, world_size, rank):
@@ -29,6 +37,19 @@ def shard_plan(height, world_size):
     return [shard_rows(height, world_size, r) for r in range(world_size)]
 
 
+def cyclic_rows(height, world_size, rank, stripe=DEFAULT_STRIPE):
+    """Row specification ``(row0, nrows, row_block, row_stride)`` of ``rank`` under the block-cyclic distribution."""
+    if world_size == 1:
+        return 0, height, 0, 0
+    return rank * stripe, len(cyclic_global_rows(height, world_size, rank, stripe)), stripe, world_size * stripe
+
+
+def cyclic_global_rows(height, world_size, rank, stripe=DEFAULT_STRIPE):
+    """Global row index of every local row of ``rank`` (ascending)."""
+    g = np.arange(height)
+    return g[(g // stripe) % world_size == rank]
+
+
 def broadcast_source(tensors, src=0, group=None):
     """Broadcast the source tensors (lon, lat, data, ...) from rank ``src`` in place; returns them."""
     import torch.distributed as dist
@@ -39,28 +60,56 @@ def broadcast_source(tensors, src=0, group=None):
     return tensors
 
 
-def all_gather_rows(local_block, height, group=None):
-    """Assemble the (height, ...) result from every rank's row block (blocks may differ in size)."""
+def _world(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def all_gather_rows(local_block, height, group=None, stripe=None):
+    """Assemble the (height, ...) result on every rank from the ranks' row sets (which may differ in size).
+
+    ``stripe=None``: contiguous blocks of ``shard_rows``; otherwise the block-cyclic rows of ``cyclic_rows``.
+    """
     import torch
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    rank, world = _world(group)
+    if world == 1:
         return local_block
-    world = dist.get_world_size(group)
-    plan = shard_plan(height, world)
-    max_rows = max(n for _, n in plan)
+    if stripe is None:
+        counts = [n for _, n in shard_plan(height, world)]
+    else:
+        counts = [len(cyclic_global_rows(height, world, r, stripe)) for r in range(world)]
+    max_rows = max(counts)
     pad = torch.zeros((max_rows,) + tuple(local_block.shape[1:]), dtype=local_block.dtype, device=local_block.device)
     pad[:local_block.shape[0]] = local_block
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=group)
-    return torch.cat([p[:n] for p, (_, n) in zip(parts, plan)], dim=0)
+    if stripe is None:
+        return torch.cat([p[:n] for p, n in zip(parts, counts)], dim=0)
+    out = torch.empty((height,) + tuple(local_block.shape[1:]), dtype=local_block.dtype, device=local_block.device)
+    for r, (p, n) in enumerate(zip(parts, counts)):
+        rows = torch.as_tensor(cyclic_global_rows(height, world, r, stripe), device=local_block.device)
+        out[rows] = p[:n]
+    return out
+
+
+def assemble_rows(blocks, height, stripe=None):
+    """Host-side assembly of per-rank numpy blocks (RowAppendableArray semantics for contiguous blocks,
+    pyresample/utils/row_appendable_array.py:23-56)."""
+    world = len(blocks)
+    if stripe is None or world == 1:
+        return np.concatenate(blocks, axis=0)
+    out = np.empty((height,) + tuple(blocks[0].shape[1:]), dtype=blocks[0].dtype)
+    for r, b in enumerate(blocks):
+        out[cyclic_global_rows(height, world, r, stripe)] = b
+    return out
 
 
 def sharded_rows_apply(block_fn, height, group=None, gather=False):
-    """Run ``block_fn(row0, nrows) -> tensor (nrows, ...)`` for this rank's row block; optionally all-gather."""
-    import torch.distributed as dist
-    rank, world = 0, 1
-    if dist.is_available() and dist.is_initialized():
-        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    """Run ``block_fn(row0, nrows) -> tensor (nrows, ...)`` for this rank's contiguous row block; optionally all-gather."""
+    rank, world = _world(group)
     row0, nrows = shard_rows(height, world, rank)
     out = block_fn(row0, nrows)
     if gather:
@@ -69,21 +118,26 @@ def sharded_rows_apply(block_fn, height, group=None, gather=False):
 
 
 def resample_nearest_sharded(source_geo_def, data, target_geo_def, radius_of_influence, fill_value=0,
-                             reduce_data=True, group=None, gather=False):
-    """``kd_tree.resample_nearest`` for this rank's row block of ``target_geo_def`` (CUDA tensors in/out).
+                             reduce_data=True, group=None, gather=False, stripe=DEFAULT_STRIPE, rank=None, world=None):
+    """``kd_tree.resample_nearest`` for this rank's rows of ``target_geo_def`` (CUDA tensors in/out).
 
-    Returns the local block ``(nrows, width[, C])`` or, with ``gather=True``, the full grid on every rank.
+    ``stripe`` rows are dealt round-robin (``stripe=None``: contiguous blocks).  Returns the local rows
+    ``(nrows, width[, C])`` or, with ``gather=True``, the full grid on every rank.  ``rank`` / ``world`` default
+    to the process group's.
     """
     from . import kd_tree
     target = geometry.as_geo_def(target_geo_def)
-
-    def block(row0, nrows):
-        return kd_tree._resample(source_geo_def, data, target, 'nn', radius_of_influence, neighbours=1,
-                                 fill_value=fill_value, reduce_data=reduce_data, _rows=(row0, nrows))
-
-    return sharded_rows_apply(block, target.shape[0], group, gather)
+    if rank is None or world is None:
+        rank, world = _world(group)
+    height = target.shape[0]
+    rows = shard_rows(height, world, rank) if stripe is None else cyclic_rows(height, world, rank, stripe)
+    out = kd_tree._resample(source_geo_def, data, target, 'nn', radius_of_influence, neighbours=1,
+                            fill_value=fill_value, reduce_data=reduce_data, _rows=rows)
+    if gather:
+        return all_gather_rows(out, height, group, stripe)
+    return out
 
 
 def concat_row_blocks(blocks):
-    """Host-side concatenation of per-rank row blocks (RowAppendableArray semantics, utils/row_appendable_array.py)."""
+    """Host-side concatenation of contiguous per-rank row blocks."""
     return np.concatenate(blocks, axis=0)

@@ -345,7 +345,10 @@ class _Source(object):
     """Device-side state of the source geometry: lon/lat, valid_input_index and the neighbour index."""
 
     def __init__(self, source_geo_def, target_geo_def, reduce_data, radius_of_influence, neighbours,
-                 exclude_mask=None, tree_dtype=None):
+                 exclude_mask=None, tree_dtype=None, need_ranks=True, cover_rows=None):
+        """``need_ranks``: keep the rank table (index_array is in rank space; the fused resample paths gather by
+        source index and do not need it).  ``cover_rows``: this rank's rows of an area target - source points that
+        cannot be within the radius of any of them are left out of the index (multi-GPU row sharding)."""
         _cabi.lib()  # fail loudly when the CUDA library or the GPU is missing: there is no CPU fallback
         source_geo_def = geometry.as_geo_def(source_geo_def)
         target_geo_def = geometry.as_geo_def(target_geo_def)
@@ -377,18 +380,59 @@ class _Source(object):
             lon_t, lat_t = _dev(lon_t, tdt), _dev(lat_t, tdt)
         handle = ctypes.c_void_p()
         excl = _dev(exclude_mask).reshape(-1) if exclude_mask is not None else None
+        cover = None
+        if cover_rows is not None and target_geo_def is not None:
+            cover = _target_cover(target_geo_def, cover_rows, radius_of_influence, tdt)
         _cabi.check(_cabi.lib().prs_index_build(_ptr(lon_t), _ptr(lat_t), lon_t.numel(), _tree_code(tdt),
                                                _ptr(self.valid), _ptr(excl), _tree_code(tdt), int(neighbours),
-                                               float(radius_of_influence), ctypes.byref(handle), _stream()))
+                                               float(radius_of_influence), _ptr(cover),
+                                               _cabi.PRS_BUILD_RANKS if need_ranks else 0, ctypes.byref(handle),
+                                               _stream()))
         self.index = _Index(handle, lon_t, lat_t)
         self.n_valid = int(self.index.n)
         if self.n_valid == 0:  # EmptyResult of _create_resample_kdtree (kd_tree.py:480-481)
             self.index = None
 
 
-def _make_target(source, target_geo_def, reduce_data, radius_of_influence, row0=0, nrows=None):
+class _TreeSpec(object):
+    """What _make_target needs to know about the source before the index exists."""
+
+    def __init__(self, tree_dtype, geo_def=None):
+        self.tree_dtype, self.geo_def = np.dtype(tree_dtype), geo_def
+
+
+def _rows_tuple(rows):
+    """(row0, nrows, row_block, row_stride) of a row specification: None, (row0, nrows) or a 4-tuple."""
+    if rows is None:
+        return 0, None, 0, 0
+    rows = tuple(int(v) for v in rows)
+    return rows + (0, 0) if len(rows) == 2 else rows
+
+
+def _target_cover(target_geo_def, rows, radius_of_influence, tree_dtype):
+    """Coverage mask (prs_target_coverage) of one rank's rows of an area target; cached on the area object."""
+    target_geo_def = geometry.as_geo_def(target_geo_def)
+    if not (geometry.is_area(target_geo_def) and getattr(target_geo_def, "lons", None) is None):
+        return None
+    torch = _torch()
+    key = (_rows_tuple(rows), float(radius_of_influence), np.dtype(tree_dtype).name, torch.cuda.current_device())
+    cache = getattr(target_geo_def, "_prs_cover_cache", None)
+    if cache is None:
+        cache = target_geo_def._prs_cover_cache = {}
+    if key not in cache:
+        tg, n, keep = _make_target(_TreeSpec(tree_dtype), target_geo_def, False, radius_of_influence, rows=rows)
+        cover = torch.empty(6 * _cabi.PRS_COVER_CELLS ** 2, dtype=torch.uint8, device="cuda")
+        _cabi.check(_cabi.lib().prs_target_coverage(ctypes.byref(tg), float(radius_of_influence), _ptr(cover), _stream()))
+        cache[key] = cover
+    return cache[key]
+
+
+def _make_target(source, target_geo_def, reduce_data, radius_of_influence, row0=0, nrows=None, rows=None):
     """Describe the query points for the C-ABI.  Returns (prs_target, n, keepalive)."""
     target_geo_def = geometry.as_geo_def(target_geo_def)
+    row_block = row_stride = 0
+    if rows is not None:
+        row0, nrows, row_block, row_stride = _rows_tuple(rows)
     tg = prs_target()
     keep = []
     tree_dt = source.tree_dtype
@@ -402,8 +446,11 @@ def _make_target(source, target_geo_def, reduce_data, radius_of_influence, row0=
         tg.proj = target_geo_def.proj_spec.cstruct
         tg.grid = _area_grid(target_geo_def)
         tg.row0, tg.nrows = int(row0), int(nrows)
+        tg.row_block, tg.row_stride = int(row_block), int(row_stride)
         tg.n = int(nrows) * int(target_geo_def.width)
         return tg, tg.n, keep
+    if row_block:
+        raise NotImplementedError("block-cyclic row ownership is implemented for AreaDefinition targets")
     lons, lats = target_geo_def.get_lonlats()
     premask = None
     if isinstance(lons, np.ma.MaskedArray) or isinstance(lats, np.ma.MaskedArray):
@@ -839,7 +886,12 @@ def _resample(source_geo_def, data, target_geo_def, resample_type,
         warnings.warn('Searching for %s neighbours in %s data points' %
                       (neighbours, source_geo_def.size), stacklevel=3)
     tensor_io = _is_tensor(data)
-    source = _Source(source_geo_def, target_geo_def, reduce_data, radius_of_influence, neighbours)
+    # the fused paths gather by source index; only arbitrary Python weight functions go through index_array
+    fused = resample_type == 'nn' or neighbours == 1 or weight_funcs is None or all(
+        _gauss_sigma_of(f) is not None for f in (weight_funcs if isinstance(weight_funcs, (list, tuple))
+                                                 else [weight_funcs]))
+    source = _Source(source_geo_def, target_geo_def, reduce_data, radius_of_influence, neighbours,
+                     need_ranks=not fused, cover_rows=_rows)
     tgt = geometry.as_geo_def(target_geo_def)
     output_shape = tuple(tgt.shape)
     n_src = int(source.lon_t.numel())
@@ -979,14 +1031,16 @@ def _resample_tensor(source, data, tgt, resample_type, radius_of_influence, neig
         raise ValueError('Mismatch between geometry and dataset')
     multi = data.dim() > 1
     channels = data.shape[1] if multi else 1
-    row0, nrows = (0, None) if rows is None else (int(rows[0]), int(rows[1]))
+    row0, nrows, _, _ = _rows_tuple(rows)
     lead = tuple(tgt.shape) if rows is None else (nrows,) + tuple(tgt.shape[1:])
     output_shape = lead + ((channels,) if multi else ())
     if fill_value is None:
         raise ValueError("fill_value=None (masked output) needs numpy input")
     if source.index is None:
         return torch.full(output_shape, fill_value, dtype=data.dtype, device="cuda")
-    tg, n_t, keep = _make_target(source, tgt, reduce_data, radius_of_influence, row0, nrows)
+    tg, n_t, keep = _make_target(source, tgt, reduce_data, radius_of_influence, rows=rows)
+    if n_t == 0:  # a rank without rows
+        return torch.empty(output_shape, dtype=data.dtype, device="cuda")
     dev_data = data.contiguous().reshape(n_src, -1)
     if resample_type == 'nn':
         row_bytes = dev_data.shape[1] * dev_data.element_size()

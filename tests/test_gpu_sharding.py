@@ -1,0 +1,58 @@
+"""Row sharding on one GPU: the ranks of a world are run one after the other (no process group) and their row sets
+are assembled; the result must equal the unsharded run bit for bit.  This exercises the block-cyclic row mapping,
+the global pixel generator and - above all - the coverage culling of the per-rank index (a source point wrongly
+dropped would change an output pixel)."""
+import numpy as np
+import pytest
+
+from helpers import jittered_swath, laea_area
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world,stripe", [(2, 8), (3, 4), (4, None), (8, 64)])
+@pytest.mark.parametrize("area_kind", ["laea", "eqc"])
+def test_sharded_equals_unsharded(cuda_lib, world, stripe, area_kind):
+    import torch
+
+    from pyresample_b200 import distributed, geometry, kd_tree
+    lon, lat = jittered_swath(400, 300, np.float32, seed=41, lon0=-20, lat0=30, dlon=50, dlat=35)
+    data = torch.from_numpy(np.random.default_rng(42).standard_normal((lon.size, 3)).astype(np.float32)).cuda()
+    swath = geometry.SwathDefinition(torch.from_numpy(lon).cuda(), torch.from_numpy(lat).cuda())
+    if area_kind == "laea":
+        area = laea_area(333, 301, half=2500000.0, lat_0=48, lon_0=5)
+    else:
+        area = geometry.AreaDefinition("w", "w", "eqc", "+proj=eqc +datum=WGS84", 720, 361,
+                                       (-20037508.342789244, -10018754.171394622, 20037508.342789244,
+                                        10018754.171394622))
+    radius = 30000
+    full = kd_tree.resample_nearest(swath, data, area, radius, fill_value=-1).cpu().numpy()
+    blocks = []
+    n_indexed = []
+    for rank in range(world):
+        blk = distributed.resample_nearest_sharded(swath, data, area, radius, fill_value=-1, stripe=stripe,
+                                                   rank=rank, world=world)
+        blocks.append(blk.cpu().numpy())
+        rows = distributed.shard_rows(area.shape[0], world, rank) if stripe is None else \
+            distributed.cyclic_rows(area.shape[0], world, rank, stripe)
+        src = kd_tree._Source(swath, area, True, radius, 1, need_ranks=False, cover_rows=rows)
+        n_indexed.append(src.index.n_indexed if src.index is not None else 0)
+    got = distributed.assemble_rows(blocks, area.shape[0], stripe)
+    assert got.shape == full.shape
+    assert np.array_equal(got, full)
+    # the per-rank indices really are smaller than the full one
+    full_src = kd_tree._Source(swath, area, True, radius, 1, need_ranks=False)
+    assert max(n_indexed) < full_src.index.n_indexed
+    assert sum(n_indexed) >= full_src.index.n_indexed * 0.5
+
+
+def test_cyclic_row_plan():
+    from pyresample_b200 import distributed
+    for h, w, s in ((3600, 8, 64), (361, 3, 4), (10, 4, 64), (1000, 2, 8)):
+        seen = np.concatenate([distributed.cyclic_global_rows(h, w, r, s) for r in range(w)])
+        assert np.array_equal(np.sort(seen), np.arange(h))
+        for r in range(w):
+            row0, nrows, blk, stride = distributed.cyclic_rows(h, w, r, s)
+            g = distributed.cyclic_global_rows(h, w, r, s)
+            local = np.arange(nrows)
+            assert np.array_equal(row0 + (local // blk) * stride + local % blk, g)

@@ -1,0 +1,178 @@
+"""Edge cases of the GPU index: cube-face edges and corners, poles, the dateline, large radii, every top-k width,
+duplicates, invalid coordinates, excluded points, tiny and degenerate inputs - always against the exhaustive C
+checker or the oracle, indices bit for bit."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import kd_tree_ref
+from oracle.knn_ref import brute_query
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kd(cuda_lib):
+    from pyresample_b200 import kd_tree
+    return kd_tree
+
+
+@pytest.fixture(scope="module")
+def geometry():
+    from pyresample_b200 import geometry
+    return geometry
+
+
+def _brute_info(lon, lat, tlon, tlat, k, radius, dtype):
+    src = kd_tree_ref.transform_lonlats(lon.astype(dtype), lat.astype(dtype))
+    tgt = kd_tree_ref.transform_lonlats(tlon.astype(dtype), tlat.astype(dtype))
+    return brute_query(src, tgt, k, radius)
+
+
+def _check_against_brute(kd, geometry, lon, lat, tlon, tlat, k, radius, dtype=np.float32):
+    """float32: ECEF coordinates are bit-identical to numpy's, so indices and distances must match exactly."""
+    swath = geometry.SwathDefinition(lon.astype(dtype), lat.astype(dtype))
+    target = geometry.SwathDefinition(tlon.astype(dtype), tlat.astype(dtype))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        vii, voi, ia, da = kd.get_neighbour_info(swath, target, radius, neighbours=k, reduce_data=False)
+    assert vii.all() and voi.all()
+    bd, bi = _brute_info(lon, lat, tlon, tlat, k, radius, dtype)
+    assert np.array_equal(ia, bi), (np.argwhere(ia != bi)[:5], k)
+    if dtype == np.float32:
+        assert np.array_equal(da, bd)
+    else:  # CUDA and libm sin/cos differ by a few ulp in float64
+        assert np.array_equal(np.isinf(da), np.isinf(bd))
+        np.testing.assert_allclose(da[np.isfinite(bd)], bd[np.isfinite(bd)], rtol=1e-9, atol=1e-6)
+
+
+# the 8 cube corners sit at lon = +-45/+-135, lat = +-35.264; edges run along lon = +-45/+-135 and between corners
+CORNERS = [(lo, la) for lo in (45., 135., -45., -135.) for la in (35.26438968, -35.26438968)]
+
+
+@pytest.mark.parametrize("k", [1, 3, 8])
+def test_cube_corners_and_edges(kd, geometry, k):
+    rng = np.random.default_rng(50)
+    lons, lats, tlons, tlats = [], [], [], []
+    for lo, la in CORNERS:
+        lons.append(lo + rng.uniform(-1.5, 1.5, 1500))
+        lats.append(la + rng.uniform(-1.5, 1.5, 1500))
+        tlons.append(lo + rng.uniform(-1.2, 1.2, 600))
+        tlats.append(la + rng.uniform(-1.2, 1.2, 600))
+    for lo in (45., -135.):  # along two vertical cube edges
+        lons.append(lo + rng.uniform(-0.3, 0.3, 3000))
+        lats.append(rng.uniform(-30, 30, 3000))
+        tlons.append(lo + rng.uniform(-0.3, 0.3, 1000))
+        tlats.append(rng.uniform(-30, 30, 1000))
+    lon, lat = np.concatenate(lons), np.concatenate(lats)
+    tlon, tlat = np.concatenate(tlons), np.concatenate(tlats)
+    for radius in (8000., 60000.):
+        _check_against_brute(kd, geometry, lon, lat, tlon, tlat, k, radius)
+
+
+@pytest.mark.parametrize("k", [1, 4])
+def test_poles_and_dateline(kd, geometry, k):
+    rng = np.random.default_rng(51)
+    lon = np.concatenate([rng.uniform(-180, 180, 4000), rng.uniform(-180, 180, 4000),
+                          rng.uniform(175, 180, 1500), rng.uniform(-180, -175, 1500), [180., -180., 0., 0.]])
+    lat = np.concatenate([rng.uniform(86, 90, 4000), rng.uniform(-90, -86, 4000),
+                          rng.uniform(-10, 10, 3000), [0., 0., 90., -90.]])
+    tlon = np.concatenate([rng.uniform(-180, 180, 1500), rng.uniform(-180, 180, 1500), rng.uniform(178, 180, 500),
+                           rng.uniform(-180, -178, 500), [180., -180., 13., -77.]])
+    tlat = np.concatenate([rng.uniform(87, 90, 1500), rng.uniform(-90, -87, 1500), rng.uniform(-8, 8, 1000),
+                           [0., 0., 90., -90.]])
+    _check_against_brute(kd, geometry, lon, lat, tlon, tlat, k, 40000.)
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 8, 13, 16, 27, 32])
+def test_every_topk_width(kd, geometry, k):
+    rng = np.random.default_rng(52)
+    lon, lat = rng.uniform(0, 6, 5000), rng.uniform(50, 55, 5000)
+    tlon, tlat = rng.uniform(-0.5, 6.5, 1200), rng.uniform(49.5, 55.5, 1200)
+    _check_against_brute(kd, geometry, lon, lat, tlon, tlat, k, 25000.)
+    _check_against_brute(kd, geometry, lon, lat, tlon, tlat, k, 25000., dtype=np.float64) if k in (1, 8) else None
+
+
+def test_large_radius_sparse_source(kd, geometry):
+    """Radius far larger than the cells and than the point spacing: block growth, phase 2 over several faces."""
+    rng = np.random.default_rng(53)
+    lon, lat = rng.uniform(-180, 180, 300), np.rad2deg(np.arcsin(rng.uniform(-1, 1, 300)))
+    tlon, tlat = rng.uniform(-180, 180, 2000), np.rad2deg(np.arcsin(rng.uniform(-1, 1, 2000)))
+    for radius in (500000., 2500000., 7000000.):
+        for k in (1, 8):
+            _check_against_brute(kd, geometry, lon, lat, tlon, tlat, k, radius)
+
+
+def test_neighbours_more_than_points_and_tiny_inputs(kd, geometry):
+    lon, lat = np.array([10.0, 10.001, 10.002]), np.array([50.0, 50.0, 50.001])
+    tlon, tlat = np.array([10.0005, 40.0]), np.array([50.0, 50.0])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        vii, voi, ia, da = kd.get_neighbour_info(geometry.SwathDefinition(lon, lat), geometry.SwathDefinition(tlon, tlat),
+                                                 10000, neighbours=8, reduce_data=False)
+        assert any("Searching" in str(x.message) for x in w)
+    assert ia.shape == (2, 8) and ia.dtype == np.uint32
+    assert set(ia[0, :3]) == {0, 1, 2} and (ia[0, 3:] == 3).all() and np.isinf(da[0, 3:]).all()
+    assert (ia[1] == 3).all() and np.isinf(da[1]).all()
+    # a single source point, a single target point
+    vii, voi, ia, da = kd.get_neighbour_info(geometry.SwathDefinition(lon[:1], lat[:1]),
+                                             geometry.SwathDefinition(tlon[:1], tlat[:1]), 10000, neighbours=1)
+    assert ia.shape == (1,) and ia[0] == 0 and da[0] < 100
+
+
+def test_invalid_coordinates_and_all_invalid(kd, geometry):
+    rng = np.random.default_rng(54)
+    lon, lat = rng.uniform(0, 5, 2000), rng.uniform(40, 45, 2000)
+    lon[::7] = np.nan
+    lat[3::11] = 91.0
+    lon[5::13] = np.inf
+    lon[1::17] = -180.0001
+    tlon, tlat = rng.uniform(0, 5, 500), rng.uniform(40, 45, 500)
+    tlon[::9] = np.nan
+    tlat[4::10] = -90.5
+    swath, target = geometry.SwathDefinition(lon, lat), geometry.SwathDefinition(tlon, tlat)
+    for k in (1, 4):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = kd.get_neighbour_info(swath, target, 30000, neighbours=k)
+            want = kd_tree_ref.get_neighbour_info(swath, target, 30000, neighbours=k)
+        for g, w_ in zip(got[:3], want[:3]):
+            assert np.array_equal(g, w_)
+        np.testing.assert_allclose(got[3], want[3], rtol=1e-9)
+    # every source point invalid -> the reference's empty info (kd_tree.py:553-563): int32 indices, distance 1.0
+    bad = geometry.SwathDefinition(np.full(10, np.nan), np.full(10, 0.0))
+    vii, voi, ia, da = kd.get_neighbour_info(bad, target, 30000, neighbours=1)
+    ovii, ovoi, oia, oda = kd_tree_ref.get_neighbour_info(bad, target, 30000, neighbours=1)
+    assert ia.dtype == oia.dtype == np.int32 and np.array_equal(ia, oia) and np.array_equal(da, oda)
+    assert not vii.any() and voi.all()
+    res = kd.resample_nearest(bad, np.arange(10.), target, 30000, fill_value=-3)
+    assert np.array_equal(res, np.full(500, -3.0))
+    with pytest.raises(ValueError):
+        kd.resample_nearest(geometry.SwathDefinition(np.zeros(0), np.zeros(0)), np.zeros(0), target, 1000)
+
+
+def test_radius_is_strict_and_zero_distance(kd, geometry):
+    """A source point exactly at the query has distance 0; a candidate at d2 == dtype(r^2) is excluded."""
+    lon, lat = np.array([10.0, 10.0, 11.0]), np.array([50.0, 50.0, 50.0])
+    tgt = geometry.SwathDefinition(np.array([10.0, 10.5]), np.array([50.0, 50.0]))
+    src = geometry.SwathDefinition(lon, lat)
+    xyz = kd_tree_ref.transform_lonlats(lon, lat)
+    txyz = kd_tree_ref.transform_lonlats(np.array([10.0, 10.5]), np.array([50.0, 50.0]))
+    d = np.sqrt(((txyz[1] - xyz[0]) ** 2).sum())
+    vii, voi, ia, da = kd.get_neighbour_info(src, tgt, float(d) * 1.01, neighbours=2, reduce_data=False)
+    assert ia[0, 0] == 0 and ia[0, 1] == 1 and da[0, 0] == 0 and da[0, 1] == 0  # duplicates: lower index first
+    bd, bi = brute_query(xyz, txyz, 2, float(d) * 1.01)
+    assert np.array_equal(ia, bi)
+    # radius slightly below the distance to every point: nothing is found for the second target
+    vii, voi, ia, da = kd.get_neighbour_info(src, tgt, float(d) * 0.999, neighbours=1, reduce_data=False)
+    bd, bi = brute_query(xyz, txyz, 1, float(d) * 0.999)
+    assert np.array_equal(ia, bi)
+
+
+def test_dense_duplicates_in_one_cell(kd, geometry):
+    """Thousands of identical points fall into one cell; top-k must list the lowest indices."""
+    lon = np.concatenate([np.full(3000, 12.5), np.random.default_rng(55).uniform(12, 13, 500)])
+    lat = np.concatenate([np.full(3000, 42.25), np.random.default_rng(56).uniform(42, 42.5, 500)])
+    tlon, tlat = np.array([12.5, 12.6]), np.array([42.25, 42.3])
+    _check_against_brute(kd, geometry, lon, lat, tlon, tlat, 8, 20000., dtype=np.float64)

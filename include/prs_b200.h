@@ -140,12 +140,15 @@ int prs_valid_mask(const void *lon, const void *lat, int64_t n, int dtype, const
  * query `mask=` (future/resamplers/nearest.py:56-67): excluded points keep their rank but are never returned.
  * tree_dtype is the dtype the ECEF coordinates and distances are computed in (kd_tree.py:536-542; the xarray
  * path always uses PRS_F64, kd_tree.py:979).  k_hint / radius_hint size the cells. */
-int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, const uint8_t *valid,
+int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, uint8_t *valid,
+                    const prs_reduce_box *box /*host, optional*/, const uint8_t *premask,
                     const uint8_t *exclude, int tree_dtype, int k_hint, double radius_hint,
                     const uint8_t *cover, int flags, prs_index **index_out, void *stream);
 /* flags for prs_index_build */
 #define PRS_BUILD_RANKS 1 /* keep the rank table: needed by prs_query (index_array is in rank space) when some
                              source points are invalid; the fused resample entry points do not need it */
+#define PRS_BUILD_COMPUTE_VALID 2 /* `valid` is an OUTPUT (may be NULL): the validity of prs_valid_mask (range test,
+                             `box`, `premask`) is evaluated inside the build instead of being read from `valid` */
 /* `cover` (optional, from prs_target_coverage): source points whose coverage cell is 0 cannot be within the
  * radius of any target point of this rank and are left out of the index (they keep their rank). */
 

@@ -23,6 +23,7 @@ _INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "prs_b200.h")
 PRS_F32, PRS_F64 = 0, 1
 PRS_TARGET_LONLAT, PRS_TARGET_AREA = 0, 1
 PRS_BUILD_RANKS = 1
+PRS_BUILD_COMPUTE_VALID = 2
 PRS_COVER_CELLS = 512
 PRS_REDUCE_ALL, PRS_REDUCE_LAT_GE, PRS_REDUCE_LAT_LE, PRS_REDUCE_BOX, PRS_REDUCE_BOX_DATELINE = 0, 1, 2, 3, 4
 
@@ -132,7 +133,8 @@ def load_library():
         L.prs_area_lonlats.argtypes = [ctypes.POINTER(prs_proj_params), ctypes.POINTER(prs_area_grid), i32,
                                        i64, i64, i64, i64, i64, i64, vp, vp, vp, vp]
         L.prs_valid_mask.argtypes = [vp, vp, i64, i32, ctypes.POINTER(prs_reduce_box), vp, vp, pi64, vp]
-        L.prs_index_build.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, dbl, vp, i32, ctypes.POINTER(vp), vp]
+        L.prs_index_build.argtypes = [vp, vp, i64, i32, vp, ctypes.POINTER(prs_reduce_box), vp, vp, i32, i32, dbl, vp,
+                                      i32, ctypes.POINTER(vp), vp]
         L.prs_target_coverage.argtypes = [ctypes.POINTER(prs_target), dbl, vp, vp]
         L.prs_index_destroy.argtypes = [vp]
         L.prs_index_info.argtypes = [vp, pi64]

@@ -59,28 +59,7 @@ __global__ void valid_mask_kernel(const T *__restrict__ lon, const T *__restrict
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    T lo = lon[i], la = lat[i];
-    bool ok = lonlat_in_range<T>(lo, la);
-    if (premask && premask[i]) ok = false;
-    // data_reduce.py:282-305; numpy promotes the float32 coordinates to float64 against the float64 bounds
-    double dlo = (double)lo, dla = (double)la;
-    switch (box.kind) {
-    case PRS_REDUCE_LAT_GE:
-        ok = ok && (dla >= box.lat_min);
-        break;
-    case PRS_REDUCE_LAT_LE:
-        ok = ok && (dla <= box.lat_max);
-        break;
-    case PRS_REDUCE_BOX:
-        ok = ok && (dla >= box.lat_min) && (dla <= box.lat_max) && (dlo >= box.lon_min) && (dlo <= box.lon_max);
-        break;
-    case PRS_REDUCE_BOX_DATELINE:
-        ok = ok && (dla >= box.lat_min) && (dla <= box.lat_max) &&
-             (((dlo >= box.lon_min) && (dlo <= 180.0)) || ((dlo <= box.lon_max) && (dlo >= -180.0)));
-        break;
-    default:
-        break;
-    }
+    bool ok = valid_predicate<T>(lon[i], lat[i], box, premask && premask[i]);
     valid[i] = ok ? 1 : 0;
 }
 
@@ -430,27 +409,29 @@ int prs_valid_mask(const void *lon, const void *lat, int64_t n, int dtype, const
     return PRS_OK;
 }
 
-int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, const uint8_t *valid, const uint8_t *exclude,
-                    int tree_dtype, int k_hint, double radius_hint, const uint8_t *cover, int flags,
-                    prs_index **index_out, void *stream)
+int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, uint8_t *valid, const prs_reduce_box *box,
+                    const uint8_t *premask, const uint8_t *exclude, int tree_dtype, int k_hint, double radius_hint,
+                    const uint8_t *cover, int flags, prs_index **index_out, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (!index_out) return fail(PRS_EINVAL, "index_out is null");
     if (n <= 0 || n >= 0xFFFFFFFFLL) return fail(PRS_EINVAL, "source size must be in [1, 2^32 - 2]");
     if (dtype != tree_dtype)
         return fail(PRS_ENOSUP, "lon/lat dtype must equal tree dtype (cast on the host side of the ABI)");
-    if (!valid) return fail(PRS_EINVAL, "valid mask is required (prs_valid_mask)");
+    if (!valid && !(flags & PRS_BUILD_COMPUTE_VALID))
+        return fail(PRS_EINVAL, "valid mask is required (prs_valid_mask) unless PRS_BUILD_COMPUTE_VALID is set");
+    if ((flags & PRS_BUILD_RANKS) && !valid) return fail(PRS_EINVAL, "PRS_BUILD_RANKS needs the valid mask buffer");
     prs_index *ix = new prs_index();
     memset(ix, 0, sizeof(*ix));
     ix->tree_dtype = tree_dtype;
     ix->n_source = n;
     int rc;
     if (tree_dtype == PRS_F32)
-        rc = index_build_t<float>((const float *)lon, (const float *)lat, n, valid, exclude, cover, flags, k_hint,
-                                  radius_hint, ix, st);
+        rc = index_build_t<float>((const float *)lon, (const float *)lat, n, valid, box, premask, exclude, cover, flags,
+                                  k_hint, radius_hint, ix, st);
     else if (tree_dtype == PRS_F64)
-        rc = index_build_t<double>((const double *)lon, (const double *)lat, n, valid, exclude, cover, flags, k_hint,
-                                   radius_hint, ix, st);
+        rc = index_build_t<double>((const double *)lon, (const double *)lat, n, valid, box, premask, exclude, cover, flags,
+                                   k_hint, radius_hint, ix, st);
     else
         rc = fail(PRS_EINVAL, "tree_dtype must be PRS_F32 or PRS_F64");
     if (rc != PRS_OK) {

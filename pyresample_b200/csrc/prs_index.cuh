@@ -87,50 +87,120 @@ struct BuildCounters {
     uint32_t n_occ;         // occupied probe cells
 };
 
-// Pass 1: ECEF of every valid point that this index needs; occupancy probe at OCC_G resolution.
-//   valid[i] == 0            -> not part of the tree at all
-//   exclude[i] (query mask)  -> keeps its rank, never returned
-//   cover (optional)         -> points whose coverage cell is 0 are beyond the radius of every target point of this
-//                               rank: skipped BEFORE the exact sin/cos (approximate intrinsics are enough because
-//                               the coverage mask is dilated by a whole cell)
+// _get_valid_input_index (kd_tree.py:406, 426-428) and the reduce_data box of data_reduce.py:282-305; numpy promotes
+// the float32 coordinates to float64 against the float64 bounds.
 template <typename T>
-__global__ void build_xyz_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n,
-                                 const uint8_t *__restrict__ valid, const uint8_t *__restrict__ exclude,
-                                 const uint8_t *__restrict__ cover, Rec<T> *__restrict__ tmp,
-                                 uint32_t *__restrict__ cellid, uint8_t *__restrict__ occ, BuildCounters *counters,
-                                 uint2 *__restrict__ block_counts)
+__device__ __forceinline__ bool valid_predicate(T lo, T la, const prs_reduce_box &box, bool premasked)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool v = i < n && valid[i];
-    bool skip = false;
-    if (v) {
-        skip = exclude && exclude[i];
-        const T lo = lon[i], la = lat[i];
-        if (!skip && cover) {
-            float slo, clo, sla, cla;
-            __sincosf((float)lo * 0.017453292f, &slo, &clo);
-            __sincosf((float)la * 0.017453292f, &sla, &cla);
-            int face, iu, iv;
-            face_cell_of(cla * clo, cla * slo, sla, PRS_COVER_CELLS, face, iu, iv);
-            skip = !cover[((size_t)face * PRS_COVER_CELLS + iv) * PRS_COVER_CELLS + iu];
-        }
-        if (!skip) {
-            T x, y, z;
-            lonlat_to_xyz(lo, la, x, y, z);
-            store_rec(tmp + i, x, y, z, (uint32_t)i);
-            float fx, fy, fz;
-            unit_f32<T>(x, y, z, fx, fy, fz);
-            int face, iu, iv;
-            face_cell_of(fx, fy, fz, OCC_G, face, iu, iv);
-            uint8_t *o = occ + (face * OCC_G + iv) * OCC_G + iu;
-            if (!*o) *o = 1;
-        }
-        // rank 0's source index: blocks run roughly in order, so almost all of them skip the atomic
-        if ((uint32_t)i < *(volatile uint32_t *)&counters->first_source) atomicMin(&counters->first_source, (uint32_t)i);
+    bool ok = lonlat_in_range<T>(lo, la) && !premasked;
+    const double dlo = (double)lo, dla = (double)la;
+    switch (box.kind) {
+    case PRS_REDUCE_LAT_GE:
+        ok = ok && (dla >= box.lat_min);
+        break;
+    case PRS_REDUCE_LAT_LE:
+        ok = ok && (dla <= box.lat_max);
+        break;
+    case PRS_REDUCE_BOX:
+        ok = ok && (dla >= box.lat_min) && (dla <= box.lat_max) && (dlo >= box.lon_min) && (dlo <= box.lon_max);
+        break;
+    case PRS_REDUCE_BOX_DATELINE:
+        ok = ok && (dla >= box.lat_min) && (dla <= box.lat_max) &&
+             (((dlo >= box.lon_min) && (dlo <= 180.0)) || ((dlo <= box.lon_max) && (dlo >= -180.0)));
+        break;
+    default:
+        break;
     }
-    if (i < n) cellid[i] = (v && !skip) ? 0u : CELL_SKIP;
-    const int nv = __syncthreads_count(v), ns = __syncthreads_count(v && skip);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = make_uint2((unsigned)nv, (unsigned)ns);
+    return ok;
+}
+
+constexpr int BUILD_TPB = 256;
+constexpr int BUILD_ITEMS = 4;  // points per thread in the build passes
+
+// Pass 1: which points are valid, which of them this index needs, and an occupancy probe at OCC_G resolution.
+//   valid (in or out)        -> 0: not part of the tree at all
+//   exclude[i] (query mask)  -> keeps its rank, never returned
+//   cover (optional)         -> points whose coverage cell is 0 are beyond the radius of every target point of
+//                               this rank
+// Only approximate coordinates (fast sin/cos intrinsics) are needed here: probe and coverage cells are tens of
+// kilometres wide and both masks carry a whole cell of slack.  The exact ECEF transform runs in pass 2, for the
+// points that are kept, once the cell size is known.
+template <typename T>
+__global__ void __launch_bounds__(BUILD_TPB)
+    build_select_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, uint8_t *__restrict__ valid,
+                        int compute_valid, const prs_reduce_box box, const uint8_t *__restrict__ premask,
+                        const uint8_t *__restrict__ exclude, const uint8_t *__restrict__ cover,
+                        uint8_t *__restrict__ keep, uint8_t *__restrict__ occ, BuildCounters *counters,
+                        uint2 *__restrict__ block_counts)
+{
+    const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * BUILD_ITEMS) + threadIdx.x;
+    int nv = 0, ns = 0;
+    uint32_t first = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < BUILD_ITEMS; ++j) {
+        const int64_t i = base + (int64_t)j * BUILD_TPB;
+        if (i >= n) continue;
+        const T lo = lon[i], la = lat[i];
+        bool v;
+        if (compute_valid) {
+            v = valid_predicate<T>(lo, la, box, premask && premask[i]);
+            if (valid) valid[i] = v ? 1 : 0;
+        } else {
+            v = valid[i] != 0;
+        }
+        bool kept = false;
+        if (v) {
+            ++nv;
+            first = min(first, (uint32_t)i);
+            bool skip = exclude && exclude[i];
+            if (!skip) {
+                float slo, clo, sla, cla;
+                __sincosf((float)lo * 0.017453292f, &slo, &clo);
+                __sincosf((float)la * 0.017453292f, &sla, &cla);
+                const float fx = cla * clo, fy = cla * slo, fz = sla;
+                int face, iu, iv;
+                if (cover) {
+                    face_cell_of(fx, fy, fz, PRS_COVER_CELLS, face, iu, iv);
+                    skip = !cover[((size_t)face * PRS_COVER_CELLS + iv) * PRS_COVER_CELLS + iu];
+                }
+                if (!skip) {
+                    face_cell_of(fx, fy, fz, OCC_G, face, iu, iv);
+                    uint8_t *o = occ + (face * OCC_G + iv) * OCC_G + iu;
+                    if (!*o) *o = 1;
+                    kept = true;
+                }
+            }
+            if (!kept) ++ns;
+        }
+        keep[i] = kept ? 1 : 0;
+    }
+    // block totals (one record per block, reduced by build_reduce_kernel: no same-address atomics storm)
+    __shared__ int s_nv[BUILD_TPB / 32], s_ns[BUILD_TPB / 32];
+    __shared__ uint32_t s_first[BUILD_TPB / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nv += __shfl_xor_sync(0xffffffffu, nv, o);
+        ns += __shfl_xor_sync(0xffffffffu, ns, o);
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_nv[threadIdx.x >> 5] = nv;
+        s_ns[threadIdx.x >> 5] = ns;
+        s_first[threadIdx.x >> 5] = first;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tv = 0, ts = 0;
+        uint32_t tf = 0xFFFFFFFFu;
+        for (int w = 0; w < BUILD_TPB / 32; ++w) {
+            tv += s_nv[w];
+            ts += s_ns[w];
+            tf = min(tf, s_first[w]);
+        }
+        block_counts[blockIdx.x] = make_uint2((unsigned)tv, (unsigned)ts);
+        // rank 0's source index: blocks run roughly in order, so almost all of them skip the atomic
+        if (tf < *(volatile uint32_t *)&counters->first_source) atomicMin(&counters->first_source, tf);
+    }
 }
 
 // Reduce the per-block counts and the occupancy probe: number of valid / skipped points, bounding rectangle (in
@@ -172,25 +242,35 @@ __device__ __forceinline__ int64_t table_key(const FaceTable &t, int face, int i
     return t.base[face] + (int64_t)(iv - t.fv0[face]) * t.fw[face] + (iu - t.fu0[face]);
 }
 
-// Pass 2: cell key of every indexed point + histogram into table[key + 1].
+// Pass 2: exact ECEF coordinates of the kept points, their cell key and the histogram into table[key + 1].
 template <typename T>
-__global__ void build_count_kernel(const Rec<T> *__restrict__ tmp, int64_t n, int G, const FaceTable ft,
-                                   uint32_t *__restrict__ cellid, uint32_t *__restrict__ table)
+__global__ void __launch_bounds__(BUILD_TPB)
+    build_xyz_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, const uint8_t *__restrict__ keep,
+                     int G, const FaceTable ft, Rec<T> *__restrict__ tmp, uint32_t *__restrict__ cellid,
+                     uint32_t *__restrict__ table)
 {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    if (cellid[j] == CELL_SKIP) return;
-    Rec<T> r = load_rec(tmp + j);
-    float fx, fy, fz;
-    unit_f32<T>(r.x, r.y, r.z, fx, fy, fz);
-    int face, iu, iv;
-    face_cell_of(fx, fy, fz, G, face, iu, iv);
-    // the table rectangle is a superset of the probe cells by construction; clamp defensively
-    iu = min(max(iu, ft.fu0[face]), ft.fu0[face] + ft.fw[face] - 1);
-    iv = min(max(iv, ft.fv0[face]), ft.fv0[face] + ft.fh[face] - 1);
-    uint32_t c = (uint32_t)table_key(ft, face, iu, iv);
-    cellid[j] = c;
-    atomicAdd(&table[c + 1], 1u);
+    const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * BUILD_ITEMS) + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < BUILD_ITEMS; ++j) {
+        const int64_t i = base + (int64_t)j * BUILD_TPB;
+        if (i >= n) continue;
+        uint32_t c = CELL_SKIP;
+        if (keep[i]) {
+            T x, y, z;
+            lonlat_to_xyz(lon[i], lat[i], x, y, z);
+            store_rec(tmp + i, x, y, z, (uint32_t)i);
+            float fx, fy, fz;
+            unit_f32<T>(x, y, z, fx, fy, fz);
+            int face, iu, iv;
+            face_cell_of(fx, fy, fz, G, face, iu, iv);
+            // the table rectangle is a superset of the probe cells by construction; clamp defensively
+            iu = min(max(iu, ft.fu0[face]), ft.fu0[face] + ft.fw[face] - 1);
+            iv = min(max(iv, ft.fv0[face]), ft.fv0[face] + ft.fh[face] - 1);
+            c = (uint32_t)table_key(ft, face, iu, iv);
+            atomicAdd(&table[c + 1], 1u);
+        }
+        cellid[i] = c;
+    }
 }
 
 // Pass 3: scatter.  table[c + 1] holds start(c) after the exclusive scan and ends as start(c + 1).
@@ -229,15 +309,20 @@ static __global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_sta
 }
 
 template <typename T>
-int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, const uint8_t *exclude,
-                  const uint8_t *cover, int flags, int k_hint, double radius_hint, prs_index *ix, cudaStream_t st)
+int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const prs_reduce_box *box,
+                  const uint8_t *premask, const uint8_t *exclude, const uint8_t *cover, int flags, int k_hint,
+                  double radius_hint, prs_index *ix, cudaStream_t st)
 {
     (void)radius_hint;
     const int TPB = 256;
     int rc = ensure_pool_configured();
     if (rc != PRS_OK) return rc;
     ix->stream = st;
-    const int64_t n_blocks = (n + TPB - 1) / TPB;
+    const int64_t n_blocks = (n + BUILD_TPB * BUILD_ITEMS - 1) / (BUILD_TPB * BUILD_ITEMS);
+    const int compute_valid = (flags & PRS_BUILD_COMPUTE_VALID) != 0;
+    prs_reduce_box bx;
+    memset(&bx, 0, sizeof(bx));
+    if (box) bx = *box;
     const size_t occ_n = 6ull * OCC_G * OCC_G;
     // scratch block: counters | rect[24] | occ[occ_n] | block_counts[n_blocks]
     uint8_t *scratch = nullptr;
@@ -263,13 +348,15 @@ int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, c
         }
         PRS_CK(cudaMemcpyAsync(scratch, &init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
-    // pass 1 (records are addressed by source index, so no rank table is needed to build)
+    // pass 1: validity, selection, occupancy probe (records are addressed by source index: no rank table needed)
     Rec<T> *tmp = nullptr;
     uint32_t *cellid = nullptr;
+    uint8_t *keep = nullptr;
     PRS_CK(cudaMallocAsync((void **)&tmp, sizeof(Rec<T>) * (size_t)n, st));
     PRS_CK(cudaMallocAsync((void **)&cellid, sizeof(uint32_t) * (size_t)n, st));
-    build_xyz_kernel<T><<<(unsigned)n_blocks, TPB, 0, st>>>(lon, lat, n, valid, exclude, cover, tmp, cellid, occ, counters,
-                                                            block_counts);
+    PRS_CK(cudaMallocAsync((void **)&keep, (size_t)n, st));
+    build_select_kernel<T><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, valid, compute_valid, bx, premask, exclude,
+                                                                     cover, keep, occ, counters, block_counts);
     PRS_CKL();
     build_reduce_kernel<<<96, TPB, 0, st>>>(occ, block_counts, n_blocks, rect_dev, counters);
     PRS_CKL();
@@ -296,6 +383,7 @@ int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, c
     if (ix->n_indexed <= 0) {
         PRS_CK(cudaFreeAsync(tmp, st));
         PRS_CK(cudaFreeAsync(cellid, st));
+        PRS_CK(cudaFreeAsync(keep, st));
         ix->n_indexed = 0;
         ix->G = COARSE;
         ix->Gc = 1;
@@ -357,14 +445,15 @@ int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, c
     PRS_CK(cudaMallocAsync((void **)&ix->cell_start, sizeof(uint32_t) * (size_t)(nf + 1), st));
     ix->bytes += sizeof(uint32_t) * (size_t)(nf + 1);
     PRS_CK(cudaMemsetAsync(ix->cell_start, 0, sizeof(uint32_t) * (size_t)(nf + 1), st));
-    build_count_kernel<T><<<(unsigned)n_blocks, TPB, 0, st>>>(tmp, n, G, ix->fine, cellid, ix->cell_start);
+    build_xyz_kernel<T><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, G, ix->fine, tmp, cellid, ix->cell_start);
     PRS_CKL();
     rc = scan_u32<uint32_t>(ix->cell_start + 1, ix->cell_start + 1, nf, 0, nullptr, st);
     if (rc != PRS_OK) return rc;
     size_t rec_bytes = sizeof(Rec<T>) * (size_t)ix->n_indexed;
     PRS_CK(cudaMallocAsync((void **)&ix->recs, rec_bytes, st));
     ix->bytes += rec_bytes;
-    build_scatter_kernel<T><<<(unsigned)n_blocks, TPB, 0, st>>>(tmp, n, cellid, ix->cell_start, (Rec<T> *)ix->recs);
+    build_scatter_kernel<T><<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, st>>>(tmp, n, cellid, ix->cell_start,
+                                                                             (Rec<T> *)ix->recs);
     PRS_CKL();
     // coarse table
     PRS_CK(cudaMallocAsync((void **)&ix->coarse_start, sizeof(uint32_t) * (size_t)(nc + 1), st));
@@ -377,6 +466,7 @@ int index_build_t(const T *lon, const T *lat, int64_t n, const uint8_t *valid, c
     if (rc != PRS_OK) return rc;
     PRS_CK(cudaFreeAsync(tmp, st));
     PRS_CK(cudaFreeAsync(cellid, st));
+    PRS_CK(cudaFreeAsync(keep, st));
     return PRS_OK;
 }
 

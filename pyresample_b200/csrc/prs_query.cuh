@@ -16,13 +16,16 @@
 
 namespace prs {
 
-constexpr int QROWS = 4;            // target rows per tile
+#ifndef PRS_QROWS
+#define PRS_QROWS 8
+#endif
+constexpr int QROWS = PRS_QROWS;    // target rows per tile
 constexpr int QWARPS = 8;           // warps per block of the classification kernel
 constexpr int STAGE_ROW_BYTES = 64; // nearest rows up to this size are staged through shared memory
 // Resident blocks per SM asked of the compiler for query_kernel (128 threads): the search is latency bound, so
 // k = 1 trades registers for occupancy (64 registers); larger top-k lists need the registers more.
 #ifndef PRS_QUERY_MIN_BLOCKS
-#define PRS_QUERY_MIN_BLOCKS(K) ((K) <= 1 ? 8 : (K) <= 4 ? 6 : (K) <= 8 ? 4 : 3)
+#define PRS_QUERY_MIN_BLOCKS(K) (((K) <= 1 ? 32 : (K) <= 4 ? 24 : (K) <= 8 ? 16 : 12) / PRS_QROWS)
 #endif
 
 // ------------------------------------------------------------------------------------------ top-k list

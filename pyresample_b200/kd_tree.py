@@ -371,8 +371,9 @@ class _Source(object):
             raise TypeError('radius_of_influence must be number')
         elif not isinstance(neighbours, int):
             raise TypeError('neighbours must be integer')
-        # the number of valid points comes back with the index build (its single host round trip)
-        self.valid, _ = _valid_mask_device(lon_t, lat_t, self.dtype, box, premask, count=False)
+        # validity (range test, reduce_data box, np.ma mask) is evaluated inside the index build; the number of
+        # valid points comes back with the build's single host round trip
+        self.valid = _torch().empty(lon_t.numel(), dtype=_torch().uint8, device="cuda")
         self.lon_t, self.lat_t = lon_t, lat_t
         tdt = np.dtype(tree_dtype) if tree_dtype is not None else self.dtype
         self.tree_dtype = tdt
@@ -383,10 +384,11 @@ class _Source(object):
         cover = None
         if cover_rows is not None and target_geo_def is not None:
             cover = _target_cover(target_geo_def, cover_rows, radius_of_influence, tdt)
+        flags = _cabi.PRS_BUILD_COMPUTE_VALID | (_cabi.PRS_BUILD_RANKS if need_ranks else 0)
         _cabi.check(_cabi.lib().prs_index_build(_ptr(lon_t), _ptr(lat_t), lon_t.numel(), _tree_code(tdt),
-                                               _ptr(self.valid), _ptr(excl), _tree_code(tdt), int(neighbours),
-                                               float(radius_of_influence), _ptr(cover),
-                                               _cabi.PRS_BUILD_RANKS if need_ranks else 0, ctypes.byref(handle),
+                                               _ptr(self.valid), ctypes.byref(box) if box is not None else None,
+                                               _ptr(premask), _ptr(excl), _tree_code(tdt), int(neighbours),
+                                               float(radius_of_influence), _ptr(cover), flags, ctypes.byref(handle),
                                                _stream()))
         self.index = _Index(handle, lon_t, lat_t)
         self.n_valid = int(self.index.n)

@@ -408,7 +408,8 @@ def test_masked_data_and_sample_from_info(kd, geometry):
 
 def test_c_abi_error_reporting(cuda_lib):
     from pyresample_b200 import _cabi
-    rc = cuda_lib.prs_index_build(None, None, 0, 0, None, None, 0, 1, 1.0, None, 0, ctypes.byref(ctypes.c_void_p()), None)
+    rc = cuda_lib.prs_index_build(None, None, 0, 0, None, None, None, None, 0, 1, 1.0, None, 0,
+                                  ctypes.byref(ctypes.c_void_p()), None)
     assert rc != 0
     with pytest.raises(_cabi.PrsError):
         _cabi.check(rc)

@@ -22,10 +22,10 @@ namespace prs {
 constexpr int QROWS = PRS_QROWS;    // target rows per tile
 constexpr int QWARPS = 8;           // warps per block of the classification kernel
 constexpr int STAGE_ROW_BYTES = 64; // nearest rows up to this size are staged through shared memory
-// Resident blocks per SM asked of the compiler for query_kernel (128 threads): the search is latency bound, so
-// k = 1 trades registers for occupancy (64 registers); larger top-k lists need the registers more.
+// Resident blocks per SM asked of the compiler for query_kernel (32 * QROWS threads): the search is latency bound,
+// so occupancy beats registers up to k = 8 (64 registers, measured on C2/C3/C5); wider top-k lists get more.
 #ifndef PRS_QUERY_MIN_BLOCKS
-#define PRS_QUERY_MIN_BLOCKS(K) (((K) <= 1 ? 32 : (K) <= 4 ? 24 : (K) <= 8 ? 16 : 12) / PRS_QROWS)
+#define PRS_QUERY_MIN_BLOCKS(K) (((K) <= 8 ? 32 : (K) <= 16 ? 24 : 16) / PRS_QROWS)
 #endif
 
 // ------------------------------------------------------------------------------------------ top-k list
@@ -450,67 +450,47 @@ __device__ __forceinline__ void copy_row(void *dst, const void *src, int bytes, 
     }
 }
 
-// _resample_with_weights (kd_tree.py:741-818) + _calculate_uncertainty (kd_tree.py:821-859) for one target
-// point and one channel.  Ta: accumulation / output dtype.  Neighbour i: source row src[i] (PRS_NONE = missing),
-// weight w[i].
-template <typename Ta, typename Td, int K>
-__device__ __forceinline__ void weighted_channel(const Td *__restrict__ data, int channels, int c, const uint32_t *src,
-                                                 const Ta *w, int k, uint32_t first_valid_source, Ta fill, Ta &res_out,
-                                                 Ta &std_out, int &count_out, bool want_uncert)
+// Load up to 4 consecutive channels of one source row (vectorised when the row start is 16-byte aligned).
+template <typename Td>
+__device__ __forceinline__ void load_channels(const Td *__restrict__ p, int nc, bool vec_ok, Td v[4])
 {
-    Ta res = 0, norm = 0;
-    Ta vals[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        if (i < k) {
-            bool missing = src[i] == PRS_NONE;
-            // missing neighbours gather new_data[0] and get weight 0 (kd_tree.py:754-759,802)
-            uint32_t row = missing ? first_valid_source : src[i];
-            Ta v = (Ta)__ldg(data + (size_t)row * channels + c);
-            Ta wt = missing ? Ar<Ta>::mul((Ta)0, w[i]) : w[i];
-            vals[i] = v;
-            res = Ar<Ta>::add(res, Ar<Ta>::mul(wt, v));
-            norm = Ar<Ta>::add(norm, wt);
+    if (vec_ok && nc == 4) {
+        if (sizeof(Td) == 4) {
+            float4 f = __ldg(reinterpret_cast<const float4 *>(p));
+            v[0] = (Td)f.x;
+            v[1] = (Td)f.y;
+            v[2] = (Td)f.z;
+            v[3] = (Td)f.w;
+        } else {
+            double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+            v[0] = (Td)a.x;
+            v[1] = (Td)a.y;
+            v[2] = (Td)b.x;
+            v[3] = (Td)b.y;
         }
-    }
-    if (norm > 0)
-        res = Ar<Ta>::div(res, norm);
-    else
-        res = fill;  // also reached for NaN norm, like numpy's boolean masks (norm > 0 is False)
-    res_out = res;
-    if (want_uncert) {
-        int count = 0;
-        Ta norm_sqr = 0, sd = 0;
+    } else {
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-            if (i < k) {
-                bool missing = src[i] == PRS_NONE;
-                Ta wt = missing ? Ar<Ta>::mul((Ta)0, w[i]) : w[i];
-                count += missing ? 0 : 1;
-                norm_sqr = Ar<Ta>::add(norm_sqr, Ar<Ta>::mul(wt, wt));
-                Ta val = missing ? Ar<Ta>::mul((Ta)0, vals[i]) : vals[i];
-                Ta dv = Ar<Ta>::sub(val, res);
-                sd = Ar<Ta>::add(sd, Ar<Ta>::mul(wt, Ar<Ta>::mul(dv, dv)));
-            }
-        }
-        count_out = count;
-        if (count > 1)
-            std_out = Ar<Ta>::sqrt(Ar<Ta>::mul(Ar<Ta>::div(norm, Ar<Ta>::sub(Ar<Ta>::mul(norm, norm), norm_sqr)), sd));
-        else
-            std_out = Ar<Ta>::nan();
+        for (int j = 0; j < 4; ++j) v[j] = j < nc ? __ldg(p + j) : (Td)0;
     }
 }
 
+// _resample_with_weights (kd_tree.py:741-818) + _calculate_uncertainty (kd_tree.py:821-859) for one target point,
+// fused behind the search.  T: distance dtype (the Gaussian is evaluated in it, kd_tree.py:165), Td: data dtype,
+// Ta: accumulation / output dtype (numpy promotion: float64 for multi-channel data, kd_tree.py:783).
+// Channels are processed four at a time so that a neighbour's row is read with 16-byte loads; per channel the
+// neighbours are accumulated in order i = 0..k-1 exactly like the reference's Python loop.
 template <typename T, typename Ta, typename Td, int K>
 __device__ __noinline__ void gauss_epilogue(const QueryParams &P, const IndexView<T> &ix, int64_t p,
                                             const TopK<T, K> &top, bool valid)
 {
-    const int C = P.channels;
+    const int C = P.channels, k = P.k;
     const bool want_uncert = P.stddev_out != nullptr;
     Ta *out = (Ta *)P.out + (size_t)p * C;
     Ta *sd_out = want_uncert ? (Ta *)P.stddev_out + (size_t)p * C : nullptr;
     Ta *cnt_out = want_uncert ? (Ta *)P.count_out + (size_t)p * C : nullptr;
-    if (!valid) {  // not in valid_output_index: fill (kd_tree.py:719-723), NaN / 0 uncertainty (kd_tree.py:865-868)
+    if (!valid || top.id[0] == PRS_NONE) {
+        // not in valid_output_index (kd_tree.py:719-723, 865-868), or no neighbour at all: every weight is zero, so
+        // norm == 0 and the pixel is the fill value whatever new_data[0] holds (kd_tree.py:807-809)
         for (int c = 0; c < C; ++c) {
             out[c] = (Ta)P.fill;
             if (want_uncert) {
@@ -520,31 +500,84 @@ __device__ __noinline__ void gauss_epilogue(const QueryParams &P, const IndexVie
         }
         return;
     }
-    T dist[K];
+    const Td *data = (const Td *)P.data;
+    const bool vec_ok = (C & 3) == 0 && ((reinterpret_cast<uintptr_t>(data) & 15) == 0);
+    T dist2w[K];  // r ** 2 with r the rounded distance; missing neighbours: distance 1 (kd_tree.py:767-768)
+    int count = 0;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-        // missing neighbours: distance 1 (kd_tree.py:767-768)
-        dist[i] = top.id[i] == PRS_NONE ? (T)1 : Ar<T>::sqrt(top.d[i]);
+        const bool missing = top.id[i] == PRS_NONE;
+        const T r = missing ? (T)1 : Ar<T>::sqrt(top.d[i]);
+        dist2w[i] = Ar<T>::mul(r, r);
+        if (i < k && !missing) ++count;
     }
-    Ta w[K];
-    for (int c = 0; c < C; ++c) {
-        if (c == 0 || !P.uniform_sigma) {
-            T s2 = (T)P.sigma2[c];  // float(sigma)**2 as a weak Python scalar -> distance dtype
+    Ta wu[K];  // weights when every channel has the same sigma
+    if (P.uniform_sigma) {
+        const T s2 = (T)P.sigma2[0];  // float(sigma)**2 as a weak Python scalar -> distance dtype
 #pragma unroll
-            for (int i = 0; i < K; ++i) {
-                // np.exp(-r ** 2 / float(sigma) ** 2) evaluated in the distance dtype (kd_tree.py:165)
-                T r2 = Ar<T>::mul(dist[i], dist[i]);
-                w[i] = (Ta)Ar<T>::exp(Ar<T>::div(-r2, s2));
+        for (int i = 0; i < K; ++i) wu[i] = (Ta)Ar<T>::exp(Ar<T>::div(-dist2w[i], s2));
+    }
+    for (int c0 = 0; c0 < C; c0 += 4) {
+        const int nc = min(4, C - c0);
+        Ta res[4] = {0, 0, 0, 0}, norm[4] = {0, 0, 0, 0};
+        T s2c[4];
+        if (!P.uniform_sigma) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s2c[j] = j < nc ? (T)P.sigma2[c0 + j] : (T)1;
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            if (i < k) {
+                const bool missing = top.id[i] == PRS_NONE;
+                // missing neighbours gather new_data[0] and get weight 0 * w (kd_tree.py:754-759, 802)
+                const uint32_t row = missing ? ix.first_valid_source : top.id[i];
+                Td v[4];
+                load_channels<Td>(data + (size_t)row * C + c0, nc, vec_ok, v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    Ta w = P.uniform_sigma ? wu[i] : (Ta)Ar<T>::exp(Ar<T>::div(-dist2w[i], s2c[j]));
+                    Ta wt = missing ? Ar<Ta>::mul((Ta)0, w) : w;
+                    res[j] = Ar<Ta>::add(res[j], Ar<Ta>::mul(wt, (Ta)v[j]));
+                    norm[j] = Ar<Ta>::add(norm[j], wt);
+                }
             }
         }
-        Ta res, sd = 0;
-        int cnt = 0;
-        weighted_channel<Ta, Td, K>((const Td *)P.data, C, c, top.id, w, P.k, ix.first_valid_source, (Ta)P.fill, res,
-                                    sd, cnt, want_uncert);
-        out[c] = res;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // norm > 0 is False for NaN as well, like numpy's boolean mask
+            res[j] = (norm[j] > 0) ? Ar<Ta>::div(res[j], norm[j]) : (Ta)P.fill;
+            if (j < nc) out[c0 + j] = res[j];
+        }
         if (want_uncert) {
-            sd_out[c] = sd;
-            cnt_out[c] = (Ta)cnt;
+            Ta nsq[4] = {0, 0, 0, 0}, sd[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                if (i < k) {
+                    const bool missing = top.id[i] == PRS_NONE;
+                    const uint32_t row = missing ? ix.first_valid_source : top.id[i];
+                    Td v[4];
+                    load_channels<Td>(data + (size_t)row * C + c0, nc, vec_ok, v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        Ta w = P.uniform_sigma ? wu[i] : (Ta)Ar<T>::exp(Ar<T>::div(-dist2w[i], s2c[j]));
+                        Ta wt = missing ? Ar<Ta>::mul((Ta)0, w) : w;
+                        nsq[j] = Ar<Ta>::add(nsq[j], Ar<Ta>::mul(wt, wt));
+                        Ta val = missing ? Ar<Ta>::mul((Ta)0, (Ta)v[j]) : (Ta)v[j];
+                        Ta dv = Ar<Ta>::sub(val, res[j]);
+                        sd[j] = Ar<Ta>::add(sd[j], Ar<Ta>::mul(wt, Ar<Ta>::mul(dv, dv)));
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nc) {
+                    sd_out[c0 + j] =
+                        count > 1 ? Ar<Ta>::sqrt(Ar<Ta>::mul(
+                                        Ar<Ta>::div(norm[j], Ar<Ta>::sub(Ar<Ta>::mul(norm[j], norm[j]), nsq[j])), sd[j]))
+                                  : Ar<Ta>::nan();
+                    cnt_out[c0 + j] = (Ta)count;
+                }
+            }
         }
     }
 }

@@ -54,7 +54,7 @@ __global__ void area_lonlats_kernel(const prs_proj_params P, const prs_area_grid
 }
 
 template <typename T>
-__global__ void valid_mask_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, const prs_reduce_box box,
+__global__ void valid_mask_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, const BoxT<T> box,
                                   const uint8_t *__restrict__ premask, uint8_t *__restrict__ valid)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,9 +383,17 @@ int prs_valid_mask(const void *lon, const void *lat, int64_t n, int dtype, const
     if (box) b = *box;
     if (n > 0) {
         if (dtype == PRS_F32)
-            valid_mask_kernel<float><<<blocks_for(n), TPB, 0, st>>>((const float *)lon, (const float *)lat, n, b, premask, valid_out);
+        {
+            BoxT<float> bf;
+            make_box(b, bf);
+            valid_mask_kernel<float><<<blocks_for(n), TPB, 0, st>>>((const float *)lon, (const float *)lat, n, bf, premask, valid_out);
+        }
         else if (dtype == PRS_F64)
-            valid_mask_kernel<double><<<blocks_for(n), TPB, 0, st>>>((const double *)lon, (const double *)lat, n, b, premask, valid_out);
+        {
+            BoxT<double> bd;
+            make_box(b, bd);
+            valid_mask_kernel<double><<<blocks_for(n), TPB, 0, st>>>((const double *)lon, (const double *)lat, n, bd, premask, valid_out);
+        }
         else
             return fail(PRS_EINVAL, "dtype must be PRS_F32 or PRS_F64");
         PRS_CKL();

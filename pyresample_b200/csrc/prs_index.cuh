@@ -87,26 +87,59 @@ struct BuildCounters {
     uint32_t n_occ;         // occupied probe cells
 };
 
-// _get_valid_input_index (kd_tree.py:406, 426-428) and the reduce_data box of data_reduce.py:282-305; numpy promotes
-// the float32 coordinates to float64 against the float64 bounds.
+// _get_valid_input_index (kd_tree.py:406, 426-428) and the reduce_data box of data_reduce.py:282-305.  numpy promotes
+// float32 coordinates to float64 against the float64 bounds; float64 conversions and compares are slow on the
+// GPU, so for float32 coordinates the bounds are rounded on the host to the float32 value that gives the identical
+// decision ((double)x >= b  <=>  x >= roundup32(b);  (double)x <= b  <=>  x <= rounddown32(b)).
+template <typename T> struct BoxT {
+    int kind;
+    T lat_min, lat_max, lon_min, lon_max;
+};
+inline float round_up_f32(double b)
+{
+    float f = (float)b;
+    if ((double)f < b) f = nextafterf(f, INFINITY);
+    return f;
+}
+inline float round_down_f32(double b)
+{
+    float f = (float)b;
+    if ((double)f > b) f = nextafterf(f, -INFINITY);
+    return f;
+}
+inline void make_box(const prs_reduce_box &b, BoxT<float> &o)
+{
+    o.kind = b.kind;
+    o.lat_min = round_up_f32(b.lat_min);
+    o.lon_min = round_up_f32(b.lon_min);
+    o.lat_max = round_down_f32(b.lat_max);
+    o.lon_max = round_down_f32(b.lon_max);
+}
+inline void make_box(const prs_reduce_box &b, BoxT<double> &o)
+{
+    o.kind = b.kind;
+    o.lat_min = b.lat_min;
+    o.lon_min = b.lon_min;
+    o.lat_max = b.lat_max;
+    o.lon_max = b.lon_max;
+}
 template <typename T>
-__device__ __forceinline__ bool valid_predicate(T lo, T la, const prs_reduce_box &box, bool premasked)
+__device__ __forceinline__ bool valid_predicate(T lo, T la, const BoxT<T> &box, bool premasked)
 {
     bool ok = lonlat_in_range<T>(lo, la) && !premasked;
-    const double dlo = (double)lo, dla = (double)la;
     switch (box.kind) {
     case PRS_REDUCE_LAT_GE:
-        ok = ok && (dla >= box.lat_min);
+        ok = ok && (la >= box.lat_min);
         break;
     case PRS_REDUCE_LAT_LE:
-        ok = ok && (dla <= box.lat_max);
+        ok = ok && (la <= box.lat_max);
         break;
     case PRS_REDUCE_BOX:
-        ok = ok && (dla >= box.lat_min) && (dla <= box.lat_max) && (dlo >= box.lon_min) && (dlo <= box.lon_max);
+        ok = ok && (la >= box.lat_min) && (la <= box.lat_max) && (lo >= box.lon_min) && (lo <= box.lon_max);
         break;
     case PRS_REDUCE_BOX_DATELINE:
-        ok = ok && (dla >= box.lat_min) && (dla <= box.lat_max) &&
-             (((dlo >= box.lon_min) && (dlo <= 180.0)) || ((dlo <= box.lon_max) && (dlo >= -180.0)));
+        ok = ok && (la >= box.lat_min) && (la <= box.lat_max) &&
+             (((lo >= box.lon_min) && (lo <= (T)180)) || ((lo <= box.lon_max) && (lo >= (T)-180)));
         break;
     default:
         break;
@@ -128,7 +161,7 @@ constexpr int BUILD_ITEMS = 4;  // points per thread in the build passes
 template <typename T>
 __global__ void __launch_bounds__(BUILD_TPB)
     build_select_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, uint8_t *__restrict__ valid,
-                        int compute_valid, const prs_reduce_box box, const uint8_t *__restrict__ premask,
+                        int compute_valid, const BoxT<T> box, const uint8_t *__restrict__ premask,
                         const uint8_t *__restrict__ exclude, const uint8_t *__restrict__ cover,
                         uint8_t *__restrict__ keep, uint8_t *__restrict__ occ, BuildCounters *counters,
                         uint2 *__restrict__ block_counts)
@@ -165,8 +198,7 @@ __global__ void __launch_bounds__(BUILD_TPB)
                 }
                 if (!skip) {
                     face_cell_of(fx, fy, fz, OCC_G, face, iu, iv);
-                    uint8_t *o = occ + (face * OCC_G + iv) * OCC_G + iu;
-                    if (!*o) *o = 1;
+                    occ[(face * OCC_G + iv) * OCC_G + iu] = 1;  // fire-and-forget; a warp's stores mostly coincide
                     kept = true;
                 }
             }
@@ -320,9 +352,11 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
     ix->stream = st;
     const int64_t n_blocks = (n + BUILD_TPB * BUILD_ITEMS - 1) / (BUILD_TPB * BUILD_ITEMS);
     const int compute_valid = (flags & PRS_BUILD_COMPUTE_VALID) != 0;
-    prs_reduce_box bx;
-    memset(&bx, 0, sizeof(bx));
-    if (box) bx = *box;
+    prs_reduce_box bx0;
+    memset(&bx0, 0, sizeof(bx0));
+    if (box) bx0 = *box;
+    BoxT<T> bx;
+    make_box(bx0, bx);
     const size_t occ_n = 6ull * OCC_G * OCC_G;
     // scratch block: counters | rect[24] | occ[occ_n] | block_counts[n_blocks]
     uint8_t *scratch = nullptr;

@@ -80,6 +80,56 @@ template <typename T> __device__ __forceinline__ void unit_f32(T x, T y, T z, fl
     fz = (float)z * invR;
 }
 
+// Low-latency read-back of a few words: a one-warp kernel copies them into mapped pinned host memory and raises a
+// sequence flag; the host spins on the flag.  This replaces cudaMemcpyAsync + cudaStreamSynchronize (whose wake-up
+// costs tens of microseconds while the GPU sits idle in the middle of the index build).
+static __global__ void publish_kernel(const uint32_t *__restrict__ src, volatile uint32_t *dst, int n_words, uint32_t seq)
+{
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[1 + i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) dst[0] = seq;
+}
+
+inline int read_back_small(const void *dev_src, void *host_dst, size_t bytes, cudaStream_t st)
+{
+    struct Mailbox {
+        volatile uint32_t *host = nullptr;
+        uint32_t *dev = nullptr;
+        uint32_t seq = 0;
+    };
+    static thread_local Mailbox mb;
+    const int n_words = (int)((bytes + 3) / 4);
+    const bool use_mailbox = n_words <= 255 && getenv("PRS_NO_MAILBOX") == nullptr;
+    if (use_mailbox && !mb.host) {
+        void *h = nullptr;
+        if (cudaHostAlloc(&h, 1024, cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer((void **)&mb.dev, h, 0) == cudaSuccess) {
+            mb.host = (volatile uint32_t *)h;
+            mb.host[0] = 0;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (use_mailbox && mb.host) {
+        const uint32_t seq = ++mb.seq ? mb.seq : ++mb.seq;  // never 0
+        publish_kernel<<<1, 64, 0, st>>>((const uint32_t *)dev_src, mb.dev, n_words, seq);
+        PRS_CKL();
+        // spin (bounded), then fall back to a blocking wait so that an error cannot hang the host
+        for (long spins = 0; mb.host[0] != seq; ++spins) {
+            if (spins > 20000000L) {
+                PRS_CK(cudaStreamSynchronize(st));
+                if (mb.host[0] != seq) return fail(PRS_ECUDA, "index build: read-back flag never arrived");
+            }
+        }
+        memcpy(host_dst, (const void *)(mb.host + 1), bytes);
+        return PRS_OK;
+    }
+    PRS_CK(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, st));
+    PRS_CK(cudaStreamSynchronize(st));
+    return PRS_OK;
+}
+
 struct BuildCounters {
     uint32_t n_valid;       // valid source points (pykdtree's .n)
     uint32_t n_skipped;     // valid but excluded (query mask) or outside this rank's target coverage
@@ -400,8 +450,8 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
         uint32_t pad[4];
         int rect[24];
     } h;
-    PRS_CK(cudaMemcpyAsync(&h, scratch, sizeof(h), cudaMemcpyDeviceToHost, st));
-    PRS_CK(cudaStreamSynchronize(st));
+    rc = read_back_small(scratch, &h, sizeof(h), st);
+    if (rc != PRS_OK) return rc;
     PRS_CK(cudaFreeAsync(scratch, st));
     ix->n_valid = h.c.n_valid;
     ix->n_indexed = (int64_t)h.c.n_valid - (int64_t)h.c.n_skipped;

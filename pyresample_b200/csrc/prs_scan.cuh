@@ -67,6 +67,49 @@ __global__ void scan_tile_apply(const In *in, int64_t n, const uint32_t *__restr
     }
 }
 
+// One block scans up to a few million items in place, chunk by chunk with a running carry: used for the second
+// level of the device-wide scan and for small tables, where a launch costs more than the work.
+constexpr int SMALL_SCAN_THREADS = 1024;
+static __global__ void __launch_bounds__(SMALL_SCAN_THREADS)
+    scan_small_kernel(uint32_t *data, int64_t n, int inclusive, uint32_t *total_out)
+{
+    __shared__ uint32_t warp_sums[SMALL_SCAN_THREADS / 32];
+    __shared__ uint32_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += SMALL_SCAN_THREADS) {
+        const int64_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? data[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_sums[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t before = carry + (warp ? warp_sums[warp - 1] : 0u) + (incl - v);
+        if (i < n) data[i] = inclusive ? before + v : before;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_sums[SMALL_SCAN_THREADS / 32 - 1];
+        __syncthreads();
+    }
+    if (total_out && threadIdx.x == 0) *total_out = carry_s;
+}
+constexpr int64_t SMALL_SCAN_MAX = 1 << 14;
+
 // Exclusive/inclusive scan of n items into out (uint32).  total_dev (optional) receives the grand total.
 // Temporary storage comes from the stream-ordered allocator.
 template <typename In>
@@ -76,6 +119,11 @@ int scan_u32(const In *in, uint32_t *out, int64_t n, int inclusive, uint32_t *to
         if (total_dev) PRS_CK(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), st));
         return PRS_OK;
     }
+    if (sizeof(In) == 4 && (const void *)in == (const void *)out && n <= SMALL_SCAN_MAX) {
+        scan_small_kernel<<<1, SMALL_SCAN_THREADS, 0, st>>>(out, n, inclusive, total_dev);
+        PRS_CKL();
+        return PRS_OK;
+    }
     int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t *sums = nullptr;
     PRS_CK(cudaMallocAsync((void **)&sums, sizeof(uint32_t) * (size_t)(tiles + 1), st));
@@ -83,9 +131,9 @@ int scan_u32(const In *in, uint32_t *out, int64_t n, int inclusive, uint32_t *to
     PRS_CKL();
     // exclusive scan of the tile sums (recursive); sums[tiles] gets the total
     uint32_t *tot = sums + tiles;
-    if (tiles == 1) {
-        PRS_CK(cudaMemcpyAsync(tot, sums, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-        PRS_CK(cudaMemsetAsync(sums, 0, sizeof(uint32_t), st));
+    if (tiles <= SMALL_SCAN_MAX) {
+        scan_small_kernel<<<1, SMALL_SCAN_THREADS, 0, st>>>(sums, tiles, 0, tot);
+        PRS_CKL();
     } else {
         int rc = scan_u32<uint32_t>(sums, sums, tiles, 0, tot, st);
         if (rc != PRS_OK) return rc;

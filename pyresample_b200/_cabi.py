@@ -95,8 +95,15 @@ def build(force=False, verbose=False, jobs=None):
         units.append((os.path.join(_SRC_DIR, "prs_query_inst.cu"), os.path.join(obj_dir, "prs_query_%s_%d.o" % (t, k)),
                       ["-DPRS_INST_T=%s" % t, "-DPRS_INST_K=%d" % k]))
 
+    # kernel experiments: PRS_BUILD_ONLY="float_1,prs_b200" recompiles just those units and relinks with the
+    # existing objects of the others (only sound while the structs shared between units are unchanged)
+    only = [s for s in os.environ.get("PRS_BUILD_ONLY", "").split(",") if s]
+
     def compile_unit(unit):
         src, obj, defs = unit
+        if only and os.path.exists(obj) and not any(os.path.basename(obj) in (o + ".o", "prs_query_" + o + ".o")
+                                                    for o in only):
+            return obj
         subprocess.check_call([nvcc] + flags + defs + ["-c", src, "-o", obj])
         return obj
 

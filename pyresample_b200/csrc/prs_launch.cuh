@@ -1,4 +1,4 @@
-// Host-side launch of the two query kernels for one (tree dtype, K) pair.  Each pair is instantiated in its own
+// Host-side launch of the query kernel(s) for one (tree dtype, K) pair.  Each pair is instantiated in its own
 // translation unit (prs_query_inst.cu, compiled once per pair, in parallel) to keep the build time down.
 #pragma once
 #include "prs_query.cuh"
@@ -14,23 +14,24 @@ template <typename T, int K, int TK> inline int launch_query_k(const QueryParams
     else
         tiles = (int64_t)P.tiles_x * ((P.nrows + QROWS - 1) / QROWS);
     if (tiles > 0x7FFFFFF0LL) return fail(PRS_ENOSUP, "target too large for one launch");
-    uint32_t *live = nullptr;  // [0] = number of live tiles, [1..] = tile ids
-    PRS_CK(cudaMallocAsync((void **)&live, sizeof(uint32_t) * (size_t)(tiles + 1), st));
-    PRS_CK(cudaMemsetAsync(live, 0, sizeof(uint32_t), st));
-    classify_kernel<T, K, TK><<<(unsigned)((tiles + QWARPS - 1) / QWARPS), QWARPS * 32, 0, st>>>(P, ix, (uint32_t)tiles, live + 1, live);
-    PRS_CKL();
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;
         PRS_CK(cudaGetDevice(&dev));
         PRS_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    // persistent-style grid: a multiple of the SM count, blocks stride over the live list
-    int64_t grid = (int64_t)n_sm * 32;
-    if (grid > tiles) grid = tiles;
-    query_kernel<T, K, TK><<<(unsigned)grid, QROWS * 32, 0, st>>>(P, ix, live + 1, live);
+    uint32_t *buf = nullptr;  // [0] = number of live tiles, [1..] = their ids
+    PRS_CK(cudaMallocAsync((void **)&buf, sizeof(uint32_t) * (size_t)(tiles + 1), st));
+    uint32_t *n_live = buf, *live = buf + 1;
+    PRS_CK(cudaMemsetAsync(n_live, 0, sizeof(uint32_t), st));
+    classify_kernel<T, K, TK><<<(unsigned)((tiles + QWARPS - 1) / QWARPS), QWARPS * 32, 0, st>>>(P, ix, (uint32_t)tiles, live, n_live);
     PRS_CKL();
-    PRS_CK(cudaFreeAsync(live, st));
+    // search: persistent-style grid, a multiple of the SM count, blocks stride over the live list
+    int64_t qgrid = (int64_t)n_sm * 32;
+    if (qgrid > tiles) qgrid = tiles;
+    query_kernel<T, K, TK><<<(unsigned)qgrid, QROWS * 32, 0, st>>>(P, ix, live, n_live);
+    PRS_CKL();
+    PRS_CK(cudaFreeAsync(buf, st));
     return PRS_OK;
 }
 

@@ -28,6 +28,11 @@ constexpr int STAGE_ROW_BYTES = 64; // nearest rows up to this size are staged t
 #define PRS_QUERY_MIN_BLOCKS(K) (((K) <= 8 ? 32 : (K) <= 16 ? 24 : 16) / PRS_QROWS)
 #endif
 
+// Records fetched together in the candidate loop of the hot path.
+#ifndef PRS_SCAN_BATCH
+#define PRS_SCAN_BATCH(K) ((K) <= 4 ? 4 : 2)
+#endif
+
 // ------------------------------------------------------------------------------------------ top-k list
 // Sorted ascending by (d2, source index): ties go to the lowest source index (BASELINE north_star).
 template <typename T, int K> struct TopK {
@@ -349,11 +354,21 @@ __device__ __forceinline__ void knn_search(const IndexView<T> &ix, T qx, T qy, T
             e2 = __ldg(row + 2 * fw + hb.u1 + 1);
         }
         const uint32_t n0 = e0 - s0, n01 = n0 + (e1 - s1), total = n01 + (e2 - s2);
+        // records are fetched PRS_SCAN_BATCH at a time before any is examined: the loads of a batch are in flight
+        // together (one load per iteration left the thread waiting a full memory round trip per candidate)
+        constexpr int B = PRS_SCAN_BATCH(K);
 #pragma unroll 1
-        for (uint32_t t = 0; t < total; ++t) {
-            const uint32_t i = t < n0 ? s0 + t : (t < n01 ? s1 + (t - n0) : s2 + (t - n01));
-            Rec<T> r = load_rec(ix.recs + i);
-            top.offer(dist2<T>(qx, qy, qz, r.x, r.y, r.z), r.idx, dub);
+        for (uint32_t t0 = 0; t0 < total; t0 += B) {
+            Rec<T> r[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const uint32_t t = min(t0 + u, total - 1);
+                const uint32_t i = t < n0 ? s0 + t : (t < n01 ? s1 + (t - n0) : s2 + (t - n01));
+                r[u] = load_rec(ix.recs + i);
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u)
+                if (t0 + u < total) top.offer(dist2<T>(qx, qy, qz, r[u].x, r[u].y, r[u].z), r[u].idx, dub);
         }
     } else {
         hb.u0 = hb.v0 = 1;  // home block outside the table: nothing visited
@@ -726,24 +741,65 @@ __device__ __forceinline__ void epilogue(const QueryParams &P, const IndexView<T
     }
 }
 
-// Kernel A: one warp per tile.  Bounds the tile's points by a spherical cap and asks the L2-resident coarse table
-// whether ANY source point lies within (cap + radius).  Tiles that see nothing get their final result right here
-// (fill value / "no neighbour" sentinels) - on wide target grids that is most of the output, written as a stream.
-// The other tiles are appended to live[] for kernel B.
-template <typename T, int K, int TK>
-__global__ void __launch_bounds__(QWARPS * 32, 4)
-    classify_kernel(const __grid_constant__ QueryParams P, const __grid_constant__ IndexView<T> ix, uint32_t n_tiles,
-                    uint32_t *__restrict__ live, uint32_t *__restrict__ n_live)
+// Classification, one warp per tile: bound the tile's points by a spherical cap and ask the L2-resident coarse table
+// whether ANY source point lies within (cap + radius).  Tiles that see nothing ("dead") get their final result
+// without a search (fill value / "no neighbour" sentinels) - on wide target grids that is most of the output,
+// written as a stream; the other tiles are listed in live[] for the search kernel.
+// tile_live: can any point of the tile have a neighbour?  vmask = this lane's valid points (bit j = tile row j).
+__device__ __forceinline__ float warp_min(float v)
 {
-    __shared__ __align__(16) unsigned char stage_all[QWARPS][32 * STAGE_ROW_BYTES];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x * QWARPS + warp;
-    if (tile >= n_tiles) return;
-    int trow0, tcol;
-    tile_origin(P, TK, tile, lane, trow0, tcol);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Cap (unit centre c, squared chord d2m) around the valid points of a tile; false when the tile has none.
+// Separable projections: the tile is the product of <= 32 longitudes (one per lane) and QROWS latitudes, and
+//   u(j,l).c = sin(lat_j) sin(lat_c) + cos(lat_j) cos(lat_c) cos(lon_l - lon_c)
+// grows with cos(lon_l - lon_c) (cos(lat) >= 0), so the farthest point of row j sits at the column with the smallest
+// cos(dlon): two warp reductions instead of a transform per point.  chord^2 = 2 - 2 u.c loses digits for small tiles;
+// the absolute slack below (a few float32 ulps of 1) only ever makes the cap larger.
+template <typename T, int TK>
+__device__ __forceinline__ bool tile_cap(const QueryParams &P, uint32_t tile, int trow0, int tcol, int lane,
+                                         unsigned &vmask, float &cx, float &cy, float &cz, float &d2m)
+{
     const float invR = (float)(1.0 / PRS_R);
+    vmask = 0;
+    if (TK == PRS_TK_AREA_SEP && !P.valid_extra) {
+        const int W = (int)P.grid.width;
+        float lc = 0.f, ls = 0.f;
+        bool col_ok = false;
+        if (tcol < W) {
+            const ColTab<T> ct = ((const ColTab<T> *)P.col_tab)[tcol];
+            lc = (float)ct.c;
+            ls = (float)ct.s;
+            col_ok = P.col_ok[tcol] != 0;
+        }
+        const int rows = min(QROWS, P.nrows - trow0);
+        float rcos = 0.f, rsin = 0.f;  // lane j < rows holds tile row j
+        bool row_ok = false;
+        if (lane < rows) {
+            const RowTab<T> rt = ((const RowTab<T> *)P.row_tab)[trow0 + lane];
+            rcos = (float)rt.rc * invR;
+            rsin = (float)rt.rz * invR;
+            row_ok = P.row_ok[trow0 + lane] != 0;
+        }
+        const unsigned rmask = __ballot_sync(0xffffffffu, row_ok), cmask = __ballot_sync(0xffffffffu, col_ok);
+        if (col_ok) vmask = rmask;
+        if (rmask == 0 || cmask == 0) return false;
+        const int jc = (rmask >> (QROWS / 2)) & 1u ? QROWS / 2 : __ffs(rmask) - 1;
+        const int lcn = (cmask >> 16) & 1u ? 16 : __ffs(cmask) - 1;
+        const float cc = __shfl_sync(0xffffffffu, lc, lcn), cs = __shfl_sync(0xffffffffu, ls, lcn);
+        const float rcc = __shfl_sync(0xffffffffu, rcos, jc), rsc = __shfl_sync(0xffffffffu, rsin, jc);
+        const float cosd = warp_min(col_ok ? lc * cc + ls * cs : 1.f);
+        const float dot = warp_min(row_ok ? rsin * rsc + rcos * rcc * cosd : 1.f);
+        cx = rcc * cc;
+        cy = rcc * cs;
+        cz = rsc;
+        d2m = fmaxf(2.f - 2.f * dot, 0.f) * 1.001f + 1e-6f;
+        return true;
+    }
     float ux[QROWS], uy[QROWS], uz[QROWS];
-    unsigned vmask = 0;
 #pragma unroll
     for (int j = 0; j < QROWS; ++j) {
         const int64_t p = tile_point(P, TK, tile, trow0, tcol, j, lane);
@@ -758,32 +814,43 @@ __global__ void __launch_bounds__(QWARPS * 32, 4)
             }
         }
     }
-    // cap centre: any valid point of the tile will do (the cap only has to contain the tile); take the first
-    // valid point of the lowest lane that has one
     const unsigned has = __ballot_sync(0xffffffffu, vmask != 0);
-    bool is_live = ix.recs != nullptr && has != 0;
+    if (has == 0) return false;
+    // cap centre: any valid point will do (the cap only has to contain the tile); prefer the middle of the tile
+    const int src_lane = (has & (1u << 16)) ? 16 : __ffs(has) - 1;
+    const int jj = (vmask & (1u << (QROWS / 2))) ? QROWS / 2 : __ffs(vmask) - 1;  // used on lanes with a point
+    float mx = 0.f, my = 0.f, mz = 0.f;
+#pragma unroll
+    for (int j = 0; j < QROWS; ++j)
+        if (j == jj) {
+            mx = ux[j];
+            my = uy[j];
+            mz = uz[j];
+        }
+    cx = __shfl_sync(0xffffffffu, mx, src_lane);
+    cy = __shfl_sync(0xffffffffu, my, src_lane);
+    cz = __shfl_sync(0xffffffffu, mz, src_lane);
+    d2m = 0.f;
+#pragma unroll
+    for (int j = 0; j < QROWS; ++j)
+        if (vmask & (1u << j)) {
+            float dx = ux[j] - cx, dy = uy[j] - cy, dz = uz[j] - cz;
+            d2m = fmaxf(d2m, dx * dx + dy * dy + dz * dz);
+        }
+    d2m = warp_max(d2m);
+    return true;
+}
+
+template <typename T, int TK>
+__device__ __forceinline__ bool tile_live(const QueryParams &P, const IndexView<T> &ix, uint32_t tile, int lane,
+                                          unsigned &vmask_out)
+{
+    int trow0, tcol;
+    tile_origin(P, TK, tile, lane, trow0, tcol);
+    unsigned vmask;
+    float cx, cy, cz, d2m;
+    bool is_live = tile_cap<T, TK>(P, tile, trow0, tcol, lane, vmask, cx, cy, cz, d2m) && ix.recs != nullptr;
     if (is_live) {
-        // prefer the point in the middle of the tile (smallest cap), else the first valid one
-        const int src_lane = (has & (1u << 16)) ? 16 : __ffs(has) - 1;
-        const int jj = (vmask & (1u << (QROWS / 2))) ? QROWS / 2 : __ffs(vmask) - 1;  // used on lanes with a point
-        float mx = 0.f, my = 0.f, mz = 0.f;
-#pragma unroll
-        for (int j = 0; j < QROWS; ++j)
-            if (j == jj) {
-                mx = ux[j];
-                my = uy[j];
-                mz = uz[j];
-            }
-        const float cx = __shfl_sync(0xffffffffu, mx, src_lane), cy = __shfl_sync(0xffffffffu, my, src_lane),
-                    cz = __shfl_sync(0xffffffffu, mz, src_lane);
-        float d2m = 0.f;
-#pragma unroll
-        for (int j = 0; j < QROWS; ++j)
-            if (vmask & (1u << j)) {
-                float dx = ux[j] - cx, dy = uy[j] - cy, dz = uz[j] - cz;
-                d2m = fmaxf(d2m, dx * dx + dy * dy + dz * dz);
-            }
-        d2m = warp_max(d2m);
         const T dub = (T)(P.radius * P.radius);
         const float sr = sqrtf(cap_s2<T>(dub));
         // chord of the union cap on the unit sphere <= tile chord + radius chord (triangle inequality)
@@ -797,12 +864,23 @@ __global__ void __launch_bounds__(QWARPS * 32, 4)
                                    bounds_inside_face(hb)) != 0;
         }
     }
-    if (is_live) {
-        if (lane == 0) live[atomicAdd(n_live, 1u)] = tile;
-        return;
-    }
-    unsigned char *stage = stage_all[warp];
-    if (P.mode == PRS_EPI_NEAREST && P.row_bytes <= STAGE_ROW_BYTES && (P.row_bytes & 3) == 0 && TK != PRS_TK_LONLAT) {
+    vmask_out = vmask;
+    return is_live;
+}
+
+__device__ __forceinline__ bool fill_is_pattern(const QueryParams &P, int TK)
+{
+    return P.mode == PRS_EPI_NEAREST && P.row_bytes <= STAGE_ROW_BYTES && (P.row_bytes & 3) == 0 && TK != PRS_TK_LONLAT;
+}
+
+// tile_fill: the result of a tile without neighbours.  vmask is only read when !fill_is_pattern().
+template <typename T, int K, int TK>
+__device__ __forceinline__ void tile_fill(const QueryParams &P, const IndexView<T> &ix, uint32_t tile, int lane,
+                                          unsigned char *stage, unsigned vmask)
+{
+    int trow0, tcol;
+    tile_origin(P, TK, tile, lane, trow0, tcol);
+    if (fill_is_pattern(P, TK)) {
         // fast path: the tile is rows of the fill pattern - stage 32 fill rows once, stream them out per tile row
         const int rb = P.row_bytes;
         copy_row(stage + lane * rb, P.fill_row, rb, P.vec);
@@ -848,6 +926,45 @@ __global__ void __launch_bounds__(QWARPS * 32, 4)
     }
 }
 
+// One live tile, one point per thread (warp w of the block takes row w of the tile).
+template <typename T, int K, int TK>
+__device__ __forceinline__ void query_tile(const QueryParams &P, const IndexView<T> &ix, uint32_t tile, int lane,
+                                           int warp, unsigned char *stage, T dub, float s2r, float sr)
+{
+    int trow, tcol;
+    tile_origin(P, TK, tile, lane, trow, tcol);
+    const int64_t p = tile_point(P, TK, tile, trow, tcol, warp, lane);
+    trow += warp;
+    T qx = 0, qy = 0, qz = 0;
+    bool valid = false;
+    if (p >= 0) valid = target_point<T, TK>(P, p, trow, tcol, qx, qy, qz);
+    TopK<T, K> top;
+    top.init();
+    if (valid) knn_search<T, K>(ix, qx, qy, qz, dub, s2r, sr, top);
+    epilogue<T, K, TK>(P, ix, p, trow, tcol, lane, stage, top, valid);
+}
+
+// Kernel A: classify each tile, fill the dead ones, list the live ones.  The fill stores (95 us of DRAM time on C2)
+// overlap the classification arithmetic of other warps inside this kernel.  Tried and rejected (slower on C1, C2,
+// C3 and C5, profiles/r1_overlap_experiments.txt): one persistent self-scheduling kernel doing classification and
+// search, and classification / fill / search as three kernels with the fill stream on a second stream.
+template <typename T, int K, int TK>
+__global__ void __launch_bounds__(QWARPS * 32, 4)
+    classify_kernel(const __grid_constant__ QueryParams P, const __grid_constant__ IndexView<T> ix, uint32_t n_tiles,
+                    uint32_t *__restrict__ live, uint32_t *__restrict__ n_live)
+{
+    __shared__ __align__(16) unsigned char stage_all[QWARPS][32 * STAGE_ROW_BYTES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * QWARPS + warp;
+    if (tile >= n_tiles) return;
+    unsigned vmask;
+    if (tile_live<T, TK>(P, ix, tile, lane, vmask)) {
+        if (lane == 0) live[atomicAdd(n_live, 1u)] = tile;
+    } else {
+        tile_fill<T, K, TK>(P, ix, tile, lane, stage_all[warp], vmask);
+    }
+}
+
 // Kernel B: the tiles that may have neighbours.  One block of QROWS warps per live tile, one point per thread.
 template <typename T, int K, int TK>
 __global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS(K))
@@ -862,17 +979,7 @@ __global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS(K))
 #pragma unroll 1
     for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) {
         const uint32_t tile = __ldg(live + t);
-        int trow, tcol;
-        tile_origin(P, TK, tile, lane, trow, tcol);
-        const int64_t p = tile_point(P, TK, tile, trow, tcol, warp, lane);
-        trow += warp;
-        T qx = 0, qy = 0, qz = 0;
-        bool valid = false;
-        if (p >= 0) valid = target_point<T, TK>(P, p, trow, tcol, qx, qy, qz);
-        TopK<T, K> top;
-        top.init();
-        if (valid) knn_search<T, K>(ix, qx, qy, qz, dub, s2r, sr, top);
-        epilogue<T, K, TK>(P, ix, p, trow, tcol, lane, stage_all[warp], top, valid);
+        query_tile<T, K, TK>(P, ix, tile, lane, warp, stage_all[warp], dub, s2r, sr);
     }
 }
 

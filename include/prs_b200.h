@@ -182,6 +182,23 @@ int prs_query(const prs_index *index, const prs_target *target, int k, double ra
 int prs_resample_nearest(const prs_index *index, const prs_target *target, double radius,
                          const void *data, int64_t row_bytes, const void *fill_row, void *out, void *stream);
 
+/* Staged form of prs_resample_nearest for area targets, for callers that overlap host<->device transfers with
+ * the kernels (pyresample_b200/kd_tree.py:_nearest_pipelined): the output of tiles that cannot have a neighbour
+ * does not depend on `data`, so it can be produced - and read back - while `data` is still being uploaded.
+ *   prs_resample_scratch_bytes: size of the device scratch buffer the two stages share (0: not an area target);
+ *   prs_resample_nearest_fill:   classifies the tiles (32 columns x PRS_TILE_ROWS rows), writes fill_row into every
+ *                                pixel of the tiles without neighbours, lists the others in scratch and sets
+ *                                tile_row_live[r] = 1 (device uint8 [ceil(nrows / PRS_TILE_ROWS)], optional) for each
+ *                                band of PRS_TILE_ROWS rows that holds such a tile - the other bands are final;
+ *   prs_resample_nearest_search: search + gather (kd_tree.py:545-548, 705-723) for the tiles listed in scratch.
+ * Both stages together write exactly what prs_resample_nearest writes. */
+#define PRS_TILE_ROWS 8
+int64_t prs_resample_scratch_bytes(const prs_target *target);
+int prs_resample_nearest_fill(const prs_index *index, const prs_target *target, double radius, int64_t row_bytes,
+                              const void *fill_row, void *out, void *scratch, uint8_t *tile_row_live, void *stream);
+int prs_resample_nearest_search(const prs_index *index, const prs_target *target, double radius, const void *data,
+                                int64_t row_bytes, const void *fill_row, void *out, void *scratch, void *stream);
+
 /* resample_gauss (kd_tree.py:113-189) fused: w = exp(-d^2 / sigma_c^2), _resample_with_weights
  * (kd_tree.py:741-818) and optionally _calculate_uncertainty (kd_tree.py:821-859).
  * data: [n_source * channels] of data_dtype (PRS_F32/PRS_F64), out/stddev/count: [n * channels] of the

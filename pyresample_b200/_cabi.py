@@ -25,11 +25,13 @@ PRS_TARGET_LONLAT, PRS_TARGET_AREA = 0, 1
 PRS_BUILD_RANKS = 1
 PRS_BUILD_COMPUTE_VALID = 2
 PRS_COVER_CELLS = 512
+PRS_TILE_ROWS = 8
 PRS_REDUCE_ALL, PRS_REDUCE_LAT_GE, PRS_REDUCE_LAT_LE, PRS_REDUCE_BOX, PRS_REDUCE_BOX_DATELINE = 0, 1, 2, 3, 4
 
 EXPORTED_SYMBOLS = (
     "prs_abi_version", "prs_last_error", "prs_launch_count", "prs_lonlat_to_xyz", "prs_area_lonlats", "prs_valid_mask",
     "prs_index_build", "prs_target_coverage", "prs_index_destroy", "prs_index_info", "prs_query", "prs_resample_nearest",
+    "prs_resample_scratch_bytes", "prs_resample_nearest_fill", "prs_resample_nearest_search",
     "prs_resample_gauss", "prs_gather_nearest", "prs_gather_weighted", "prs_compact_rows",
     "prs_rank_to_source", "prs_scatter_rows",
 )
@@ -147,6 +149,10 @@ def load_library():
         L.prs_index_info.argtypes = [vp, pi64]
         L.prs_query.argtypes = [vp, ctypes.POINTER(prs_target), i32, dbl, vp, vp, vp, pi64, vp]
         L.prs_resample_nearest.argtypes = [vp, ctypes.POINTER(prs_target), dbl, vp, i64, vp, vp, vp]
+        L.prs_resample_scratch_bytes.restype = i64
+        L.prs_resample_scratch_bytes.argtypes = [ctypes.POINTER(prs_target)]
+        L.prs_resample_nearest_fill.argtypes = [vp, ctypes.POINTER(prs_target), dbl, i64, vp, vp, vp, vp, vp]
+        L.prs_resample_nearest_search.argtypes = [vp, ctypes.POINTER(prs_target), dbl, vp, i64, vp, vp, vp, vp]
         L.prs_resample_gauss.argtypes = [vp, ctypes.POINTER(prs_target), i32, dbl, vp, i32, i32,
                                          ctypes.POINTER(ctypes.c_double), dbl, vp, vp, vp, pi64, vp]
         L.prs_gather_nearest.argtypes = [vp, i64, ctypes.c_uint32, vp, vp, i64, vp, vp, vp]
@@ -157,7 +163,7 @@ def load_library():
         L.prs_rank_to_source.argtypes = [vp, i64, vp, pi64, vp]
         L.prs_scatter_rows.argtypes = [vp, i64, i64, vp, vp, vp, vp]
         for name in EXPORTED_SYMBOLS:
-            if name not in ("prs_abi_version", "prs_last_error", "prs_launch_count"):
+            if name not in ("prs_abi_version", "prs_last_error", "prs_launch_count", "prs_resample_scratch_bytes"):
                 getattr(L, name).restype = i32
         _lib = L
         return L

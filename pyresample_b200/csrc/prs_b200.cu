@@ -541,6 +541,54 @@ int prs_resample_nearest(const prs_index *index, const prs_target *target, doubl
     return launch_query(P, index, target, st);
 }
 
+int64_t prs_resample_scratch_bytes(const prs_target *target)
+{
+    if (!target || target->kind != PRS_TARGET_AREA) return 0;
+    const int64_t tiles = ((target->grid.width + 31) / 32) * ((target->nrows + PRS_TILE_ROWS - 1) / PRS_TILE_ROWS);
+    return (int64_t)sizeof(uint32_t) * (tiles + 1);
+}
+
+static int resample_nearest_stage(int stage, const prs_index *index, const prs_target *target, double radius,
+                                  const void *data, int64_t row_bytes, const void *fill_row, void *out, void *scratch,
+                                  uint8_t *tile_row_live, cudaStream_t st)
+{
+    static_assert(PRS_TILE_ROWS == prs::QROWS, "PRS_TILE_ROWS of the header is the kernels' tile height");
+    if (!target || target->kind != PRS_TARGET_AREA) return fail(PRS_ENOSUP, "staged resampling needs an area target");
+    if (!fill_row || !out || !scratch || row_bytes <= 0 || row_bytes > 0x7FFFFFF0LL) return fail(PRS_EINVAL, "bad fill/out/scratch");
+    if (stage == 2 && !data) return fail(PRS_EINVAL, "data is null");
+    QueryParams P;
+    memset(&P, 0, sizeof(P));
+    P.radius = radius;
+    P.k = 1;
+    P.mode = PRS_EPI_NEAREST;
+    P.data = data;
+    P.fill_row = fill_row;
+    P.out = out;
+    P.row_bytes = (int)row_bytes;
+    P.vec = pick_vec(row_bytes, data ? data : fill_row, fill_row, out);
+    P.stage = stage;
+    P.scratch = (uint32_t *)scratch;
+    if (stage == 1 && tile_row_live) {
+        P.tile_row_live = tile_row_live;
+        PRS_CK(cudaMemsetAsync(tile_row_live, 0, (size_t)((target->nrows + PRS_TILE_ROWS - 1) / PRS_TILE_ROWS), st));
+    }
+    return launch_query(P, index, target, st);
+}
+
+int prs_resample_nearest_fill(const prs_index *index, const prs_target *target, double radius, int64_t row_bytes,
+                              const void *fill_row, void *out, void *scratch, uint8_t *tile_row_live, void *stream)
+{
+    return resample_nearest_stage(1, index, target, radius, nullptr, row_bytes, fill_row, out, scratch, tile_row_live,
+                                  (cudaStream_t)stream);
+}
+
+int prs_resample_nearest_search(const prs_index *index, const prs_target *target, double radius, const void *data,
+                                int64_t row_bytes, const void *fill_row, void *out, void *scratch, void *stream)
+{
+    return resample_nearest_stage(2, index, target, radius, data, row_bytes, fill_row, out, scratch, nullptr,
+                                  (cudaStream_t)stream);
+}
+
 int prs_resample_gauss(const prs_index *index, const prs_target *target, int k, double radius, const void *data,
                        int data_dtype, int channels, const double *sigmas_host, double fill, void *out, void *stddev_out,
                        void *count_out, int64_t *flags_host, void *stream)

@@ -20,18 +20,23 @@ template <typename T, int K, int TK> inline int launch_query_k(const QueryParams
         PRS_CK(cudaGetDevice(&dev));
         PRS_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    uint32_t *buf = nullptr;  // [0] = number of live tiles, [1..] = their ids
-    PRS_CK(cudaMallocAsync((void **)&buf, sizeof(uint32_t) * (size_t)(tiles + 1), st));
+    uint32_t *buf = P.scratch;  // [0] = number of live tiles, [1..] = their ids
+    if (P.stage == 0) PRS_CK(cudaMallocAsync((void **)&buf, sizeof(uint32_t) * (size_t)(tiles + 1), st));
+    if (!buf) return fail(PRS_EINVAL, "staged call without scratch");
     uint32_t *n_live = buf, *live = buf + 1;
-    PRS_CK(cudaMemsetAsync(n_live, 0, sizeof(uint32_t), st));
-    classify_kernel<T, K, TK><<<(unsigned)((tiles + QWARPS - 1) / QWARPS), QWARPS * 32, 0, st>>>(P, ix, (uint32_t)tiles, live, n_live);
-    PRS_CKL();
-    // search: persistent-style grid, a multiple of the SM count, blocks stride over the live list
-    int64_t qgrid = (int64_t)n_sm * 32;
-    if (qgrid > tiles) qgrid = tiles;
-    query_kernel<T, K, TK><<<(unsigned)qgrid, QROWS * 32, 0, st>>>(P, ix, live, n_live);
-    PRS_CKL();
-    PRS_CK(cudaFreeAsync(buf, st));
+    if (P.stage != 2) {
+        PRS_CK(cudaMemsetAsync(n_live, 0, sizeof(uint32_t), st));
+        classify_kernel<T, K, TK><<<(unsigned)((tiles + QWARPS - 1) / QWARPS), QWARPS * 32, 0, st>>>(P, ix, (uint32_t)tiles, live, n_live);
+        PRS_CKL();
+    }
+    if (P.stage != 1) {
+        // search: persistent-style grid, a multiple of the SM count, blocks stride over the live list
+        int64_t qgrid = (int64_t)n_sm * 32;
+        if (qgrid > tiles) qgrid = tiles;
+        query_kernel<T, K, TK><<<(unsigned)qgrid, QROWS * 32, 0, st>>>(P, ix, live, n_live);
+        PRS_CKL();
+    }
+    if (P.stage == 0) PRS_CK(cudaFreeAsync(buf, st));
     return PRS_OK;
 }
 

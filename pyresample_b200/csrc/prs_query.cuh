@@ -439,6 +439,11 @@ struct QueryParams {
     int uniform_sigma;
     double fill;
     void *stddev_out, *count_out;
+    // staged execution (prs_resample_nearest_fill / _search): 0 = classify + fill + search in one call,
+    // 1 = classify + fill only (live tiles listed in scratch), 2 = search the tiles listed in scratch
+    int stage;
+    uint32_t *scratch;       // caller-owned: [0] = number of live tiles, [1..] = their ids
+    uint8_t *tile_row_live;  // stage 1: [tile row] = 1 when the tile row holds a live tile
 };
 
 __device__ __forceinline__ void copy_row(void *dst, const void *src, int bytes, int vec)
@@ -959,7 +964,10 @@ __global__ void __launch_bounds__(QWARPS * 32, 4)
     if (tile >= n_tiles) return;
     unsigned vmask;
     if (tile_live<T, TK>(P, ix, tile, lane, vmask)) {
-        if (lane == 0) live[atomicAdd(n_live, 1u)] = tile;
+        if (lane == 0) {
+            live[atomicAdd(n_live, 1u)] = tile;
+            if (P.tile_row_live && TK != PRS_TK_LONLAT) P.tile_row_live[tile / (uint32_t)P.tiles_x] = 1;
+        }
     } else {
         tile_fill<T, K, TK>(P, ix, tile, lane, stage_all[warp], vmask);
     }

@@ -94,6 +94,83 @@ def _host(t):
     return h.numpy()
 
 
+# Outputs at least this large take the pipelined path of resample_nearest (numpy in, area target, numpy out).
+_PIPELINE_MIN_BYTES = 32 << 20
+_PIPELINE_MIN_RUN_BYTES = 4 << 20   # shorter runs of finished bands are not worth a copy of their own
+_side = {}
+
+
+def _side_streams():
+    """(upload, read-back) streams of the current device for the pipelined path."""
+    torch = _torch()
+    dev = torch.cuda.current_device()
+    if dev not in _side:
+        _side[dev] = (torch.cuda.Stream(), torch.cuda.Stream())
+    return _side[dev]
+
+
+def _band_runs(live, band_rows, nrows, row_bytes_total, min_run_bytes):
+    """Split the tile-row flags into runs [(row0, row1, is_live)]; short finished runs are merged into live ones."""
+    live = np.asarray(live, dtype=bool).copy()
+    n = live.size
+    edges = np.flatnonzero(np.diff(live.astype(np.int8))) + 1
+    starts = np.concatenate([[0], edges])
+    ends = np.concatenate([edges, [n]])
+    for b0, b1 in zip(starts, ends):
+        if not live[b0] and (min(b1 * band_rows, nrows) - b0 * band_rows) * row_bytes_total < min_run_bytes:
+            live[b0:b1] = True
+    edges = np.flatnonzero(np.diff(live.astype(np.int8))) + 1
+    starts = np.concatenate([[0], edges])
+    ends = np.concatenate([edges, [n]])
+    return [(int(b0) * band_rows, int(min(b1 * band_rows, nrows)), bool(live[b0])) for b0, b1 in zip(starts, ends)]
+
+
+def _nearest_pipelined(L, source, tg, n_t, host_rows, fill_row_host, radius):
+    """resample_nearest for host arrays with the PCIe transfers overlapped (both directions at once).
+
+    The result of every tile that cannot have a neighbour is the fill value whatever the data are, so: upload the
+    data on a side stream; meanwhile classify + fill (prs_resample_nearest_fill) and start reading back the bands
+    of rows that are already final; when the data have arrived, search the remaining tiles
+    (prs_resample_nearest_search) and read back the other bands.  Output identical to prs_resample_nearest.
+    """
+    torch = _torch()
+    main = torch.cuda.current_stream()
+    up, down = _side_streams()
+    row_bytes = host_rows.shape[1]
+    width, nrows = int(tg.grid.width), int(tg.nrows)
+    up.wait_stream(main)
+    with torch.cuda.stream(up):
+        dev_data = _dev(host_rows)
+        data_ready = torch.cuda.Event()
+        data_ready.record(up)
+    fill_row = _dev(fill_row_host)
+    out = torch.empty((n_t, row_bytes), dtype=torch.uint8, device="cuda")
+    scratch = torch.empty(int(L.prs_resample_scratch_bytes(ctypes.byref(tg))), dtype=torch.uint8, device="cuda")
+    n_bands = (nrows + _cabi.PRS_TILE_ROWS - 1) // _cabi.PRS_TILE_ROWS
+    band_live = torch.empty(n_bands, dtype=torch.uint8, device="cuda")
+    handle = source.index.handle
+    _cabi.check(L.prs_resample_nearest_fill(handle, ctypes.byref(tg), float(radius), row_bytes, _ptr(fill_row),
+                                            _ptr(out), _ptr(scratch), _ptr(band_live), _stream()))
+    host_out = torch.empty((n_t, row_bytes), dtype=torch.uint8, pin_memory=True)
+    runs = _band_runs(_host(band_live), _cabi.PRS_TILE_ROWS, nrows, width * row_bytes, _PIPELINE_MIN_RUN_BYTES)
+    down.wait_stream(main)
+    with torch.cuda.stream(down):
+        for r0, r1, is_live in runs:
+            if not is_live:
+                host_out[r0 * width:r1 * width].copy_(out[r0 * width:r1 * width], non_blocking=True)
+    main.wait_event(data_ready)
+    _cabi.check(L.prs_resample_nearest_search(handle, ctypes.byref(tg), float(radius), _ptr(dev_data), row_bytes,
+                                              _ptr(fill_row), _ptr(out), _ptr(scratch), _stream()))
+    down.wait_stream(main)
+    with torch.cuda.stream(down):
+        for r0, r1, is_live in runs:
+            if is_live:
+                host_out[r0 * width:r1 * width].copy_(out[r0 * width:r1 * width], non_blocking=True)
+    down.synchronize()
+    main.synchronize()
+    return host_out.numpy()
+
+
 def _tree_code(np_dtype):
     np_dtype = np.dtype(np_dtype)
     if np_dtype == np.float32:
@@ -941,13 +1018,19 @@ def _resample(source_geo_def, data, target_geo_def, resample_type,
     if resample_type == 'nn' or neighbours == 1:
         if neighbours != 1:
             raise ValueError('index_array contains more neighbours than just the nearest')
-        dev_data = _dev(_byte_rows(new_data))
-        row_bytes = dev_data.shape[1]
-        fill_row = _dev(_byte_rows(np.full((1, channels), fill_value, dtype=new_data.dtype)))
-        out = torch.empty((n_t, row_bytes), dtype=torch.uint8, device="cuda")
-        _cabi.check(L.prs_resample_nearest(source.index.handle, ctypes.byref(tg), float(radius_of_influence),
-                                           _ptr(dev_data), row_bytes, _ptr(fill_row), _ptr(out), _stream()))
-        result = _host(out).view(new_data.dtype)
+        host_rows = _byte_rows(new_data)
+        row_bytes = host_rows.shape[1]
+        fill_row_host = _byte_rows(np.full((1, channels), fill_value, dtype=new_data.dtype))
+        if tg.kind == PRS_TARGET_AREA and n_t * row_bytes >= _PIPELINE_MIN_BYTES:
+            result = _nearest_pipelined(L, source, tg, n_t, host_rows, fill_row_host,
+                                        radius_of_influence).view(new_data.dtype)
+        else:
+            dev_data = _dev(host_rows)
+            fill_row = _dev(fill_row_host)
+            out = torch.empty((n_t, row_bytes), dtype=torch.uint8, device="cuda")
+            _cabi.check(L.prs_resample_nearest(source.index.handle, ctypes.byref(tg), float(radius_of_influence),
+                                               _ptr(dev_data), row_bytes, _ptr(fill_row), _ptr(out), _stream()))
+            result = _host(out).view(new_data.dtype)
         if with_uncert:
             raise TypeError("uncertainty estimates need more than one neighbour")
     else:

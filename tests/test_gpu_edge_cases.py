@@ -176,3 +176,28 @@ def test_dense_duplicates_in_one_cell(kd, geometry):
     lat = np.concatenate([np.full(3000, 42.25), np.random.default_rng(56).uniform(42, 42.5, 500)])
     tlon, tlat = np.array([12.5, 12.6]), np.array([42.25, 42.3])
     _check_against_brute(kd, geometry, lon, lat, tlon, tlat, 8, 20000., dtype=np.float64)
+
+
+@pytest.mark.parametrize("min_run", [0, 1 << 40])
+def test_pipelined_nearest_equals_plain(kd, geometry, monkeypatch, min_run):
+    """The staged C-ABI calls (fill, then search) with overlapped transfers give exactly the one-call result."""
+    rng = np.random.default_rng(57)
+    lon = rng.uniform(-20, 40, 120000).astype(np.float32)
+    lat = rng.uniform(10, 40, 120000).astype(np.float32)
+    data = rng.normal(size=(120000, 3)).astype(np.float32)
+    swath = geometry.SwathDefinition(lon, lat)
+    area = geometry.AreaDefinition("g", "g", "g", "+proj=eqc +datum=WGS84", 1400, 611,
+                                   (-10018754.17, -8000000.0, 10018754.17, 9000000.0))
+    plain = kd.resample_nearest(swath, data, area, 30000, fill_value=-1)
+    monkeypatch.setattr(kd, "_PIPELINE_MIN_BYTES", 0)
+    monkeypatch.setattr(kd, "_PIPELINE_MIN_RUN_BYTES", min_run)
+    piped = kd.resample_nearest(swath, data, area, 30000, fill_value=-1)
+    assert piped.shape == plain.shape == (611, 1400, 3)
+    assert np.array_equal(piped, plain)
+    assert (plain != -1).any() and (plain[:8] == -1).all()
+    want = kd_tree_ref.resample_nearest(swath, data, area, 30000, fill_value=-1)
+    assert np.array_equal(piped, want)
+    # masked result (fill_value=None) goes through the same path
+    masked = kd.resample_nearest(swath, data[:, 0], area, 30000, fill_value=None)
+    want_m = kd_tree_ref.resample_nearest(swath, data[:, 0], area, 30000, fill_value=None)
+    assert np.array_equal(masked.mask, want_m.mask) and np.array_equal(masked.filled(0), want_m.filled(0))

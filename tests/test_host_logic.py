@@ -131,3 +131,17 @@ def test_ctypes_target_struct_roundtrip():
     tg.grid = prs_area_grid(7200, 3600, 5566.0, 5566.0, -2e7, 1e7)
     tg.row0, tg.nrows, tg.n = 450, 450, 450 * 7200
     assert tg.grid.width == 7200 and ctypes.sizeof(tg) % 8 == 0
+
+
+def test_band_runs_of_the_pipelined_path():
+    """Tile-row flags -> runs of rows to read back early (finished) or late (live); short finished runs merge."""
+    from pyresample_b200.kd_tree import _band_runs
+    live = np.array([0, 0, 0, 1, 1, 0, 1, 0, 0, 0], dtype=np.uint8)
+    runs = _band_runs(live, 8, 77, 100, 0)
+    assert runs == [(0, 24, False), (24, 40, True), (40, 48, False), (48, 56, True), (56, 77, False)]
+    assert sum(r1 - r0 for r0, r1, _ in runs) == 77
+    # a finished run of one band (8 rows * 100 bytes) is below a 1000-byte minimum -> merged with its neighbours
+    runs = _band_runs(live, 8, 77, 100, 1000)
+    assert runs == [(0, 24, False), (24, 56, True), (56, 77, False)]
+    assert _band_runs(np.zeros(4, np.uint8), 8, 32, 10, 0) == [(0, 32, False)]
+    assert _band_runs(np.ones(1, np.uint8), 8, 5, 10, 0) == [(0, 5, True)]

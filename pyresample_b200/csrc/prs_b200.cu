@@ -476,8 +476,8 @@ int prs_index_destroy(prs_index *ix)
     if (!ix) return PRS_OK;
     // stream-ordered: blocks return to the pool once the work already queued on the build stream has finished
     if (ix->recs) cudaFreeAsync(ix->recs, ix->stream);
-    if (ix->cell_start) cudaFreeAsync(ix->cell_start, ix->stream);
-    if (ix->coarse_start) cudaFreeAsync(ix->coarse_start, ix->stream);
+    if (ix->cell_alloc) cudaFreeAsync(ix->cell_alloc, ix->stream);
+    if (ix->coarse_alloc) cudaFreeAsync(ix->coarse_alloc, ix->stream);
     if (ix->rank) cudaFreeAsync(ix->rank, ix->stream);
     delete ix;
     return PRS_OK;

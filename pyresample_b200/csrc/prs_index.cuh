@@ -12,6 +12,8 @@
 #pragma once
 #include "prs_common.cuh"
 #include "prs_scan.cuh"
+#include <chrono>
+#include <mutex>
 
 namespace prs {
 
@@ -37,8 +39,9 @@ struct prs_index {
     int all_valid;       // rank == source index
     uint32_t first_valid_source;  // raveled index of rank 0 (kd_tree.py:754-759 gathers new_data[0] for missing)
     void *recs;
-    uint32_t *cell_start;
-    uint32_t *coarse_start;
+    uint32_t *cell_start;    // = cell_alloc + 3
+    uint32_t *coarse_start;  // = coarse_alloc + 3
+    uint32_t *cell_alloc, *coarse_alloc;
     uint32_t *rank;
     prs::FaceTable fine, coarse;
     int64_t n_cells, n_coarse;
@@ -80,9 +83,9 @@ template <typename T> __device__ __forceinline__ void unit_f32(T x, T y, T z, fl
     fz = (float)z * invR;
 }
 
-// Low-latency read-back of a few words: a one-warp kernel copies them into mapped pinned host memory and raises a
-// sequence flag; the host spins on the flag.  This replaces cudaMemcpyAsync + cudaStreamSynchronize (whose wake-up
-// costs tens of microseconds while the GPU sits idle in the middle of the index build).
+// Read-back of a few words: cudaMemcpyAsync + cudaStreamSynchronize by default.  Optional low-latency variant
+// (PRS_MAILBOX=1): a one-warp kernel copies them into mapped pinned host memory and raises a sequence flag, the
+// host spins on the flag.
 static __global__ void publish_kernel(const uint32_t *__restrict__ src, volatile uint32_t *dst, int n_words, uint32_t seq)
 {
     for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[1 + i] = src[i];
@@ -100,7 +103,13 @@ inline int read_back_small(const void *dev_src, void *host_dst, size_t bytes, cu
     };
     static thread_local Mailbox mb;
     const int n_words = (int)((bytes + 3) / 4);
-    const bool use_mailbox = n_words <= 255 && getenv("PRS_NO_MAILBOX") == nullptr;
+    // opt-in (PRS_MAILBOX=1): it saves ~10 us per build, but with NVML clock queries running next to it (bench.py's
+    // sampler, any monitoring agent) the flag write was seen to arrive tens of milliseconds late
+    static const bool mailbox_enabled = [] {
+        const char *e = getenv("PRS_MAILBOX");
+        return e && e[0] == '1';
+    }();
+    const bool use_mailbox = n_words <= 255 && mailbox_enabled;
     if (use_mailbox && !mb.host) {
         void *h = nullptr;
         if (cudaHostAlloc(&h, 1024, cudaHostAllocMapped) == cudaSuccess &&
@@ -197,6 +206,76 @@ __device__ __forceinline__ bool valid_predicate(T lo, T la, const BoxT<T> &box, 
     return ok;
 }
 
+// Temporaries of the build (scratch counters, unsorted records, keep flags) live in one grow-only buffer per
+// device that stays allocated between builds.  Taking 100 MB-class temporaries from the stream-ordered pool on
+// every build made the pool re-map memory for the long-lived arrays every few calls (1.5 ms inside cudaMallocAsync,
+// seen on C3); with the temporaries out of the way the pool only ever sees the same three long-lived sizes.
+// A build holds the buffer (mutex) while it queues its kernels; the next user waits on the event recorded behind
+// the last kernel that touched it, so builds on different streams stay correctly ordered.
+struct BuildWorkspace {
+    std::mutex lock;
+    void *buf = nullptr;
+    size_t capacity = 0;
+    cudaEvent_t last_use = nullptr;
+    bool used = false;
+};
+inline BuildWorkspace &build_workspace(int dev)
+{
+    static BuildWorkspace per_device[64];
+    return per_device[dev < 0 || dev >= 64 ? 0 : dev];
+}
+// RAII: acquire() takes the mutex and makes `st` wait for the previous user; the destructor records the event.
+struct WorkspaceLease {
+    BuildWorkspace *ws = nullptr;
+    cudaStream_t st = nullptr;
+    int acquire(size_t bytes, cudaStream_t stream, void **out)
+    {
+        int dev = 0;
+        PRS_CK(cudaGetDevice(&dev));
+        ws = &build_workspace(dev);
+        ws->lock.lock();
+        st = stream;
+        if (!ws->last_use) PRS_CK(cudaEventCreateWithFlags(&ws->last_use, cudaEventDisableTiming));
+        if (ws->used) PRS_CK(cudaStreamWaitEvent(st, ws->last_use, 0));
+        if (ws->capacity < bytes) {
+            if (ws->buf) {
+                PRS_CK(cudaEventSynchronize(ws->last_use));
+                PRS_CK(cudaFree(ws->buf));
+                ws->buf = nullptr;
+                ws->capacity = 0;
+            }
+            const size_t want = bytes + bytes / 8;  // a little headroom: sizes of successive swaths differ slightly
+            PRS_CK(cudaMalloc(&ws->buf, want));
+            ws->capacity = want;
+        }
+        *out = ws->buf;
+        return PRS_OK;
+    }
+    ~WorkspaceLease()
+    {
+        if (!ws) return;
+        if (ws->last_use && cudaEventRecord(ws->last_use, st) == cudaSuccess) ws->used = true;
+        ws->lock.unlock();
+    }
+};
+
+// PRS_BUILD_TIMING=1: host-side time stamps of the build on stderr (where does the host wait?)
+struct BuildTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    BuildTimer() : t0(std::chrono::steady_clock::now())
+    {
+        static const bool enabled = getenv("PRS_BUILD_TIMING") != nullptr;
+        on = enabled;
+    }
+    void mark(const char *what)
+    {
+        if (!on) return;
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[prs build] %-28s %9.1f us\n", what, us);
+    }
+};
+
 constexpr int BUILD_TPB = 256;
 constexpr int BUILD_ITEMS = 4;  // points per thread in the build passes
 
@@ -216,30 +295,44 @@ __global__ void __launch_bounds__(BUILD_TPB)
                         uint8_t *__restrict__ keep, uint8_t *__restrict__ occ, BuildCounters *counters,
                         uint2 *__restrict__ block_counts)
 {
+    // a warp works on 32 consecutive points at a time (their cells mostly coincide, so its occupancy stores and
+    // the histogram atomics of pass 2 collapse into one or two transactions); all loads are issued first
     const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * BUILD_ITEMS) + threadIdx.x;
     int nv = 0, ns = 0;
     uint32_t first = 0xFFFFFFFFu;
+    T lo[BUILD_ITEMS], la[BUILD_ITEMS];
+    uint8_t vin[BUILD_ITEMS], ex[BUILD_ITEMS];
+#pragma unroll
+    for (int j = 0; j < BUILD_ITEMS; ++j) {
+        const int64_t i = base + (int64_t)j * BUILD_TPB;
+        lo[j] = la[j] = 0;
+        vin[j] = ex[j] = 0;
+        if (i < n) {
+            lo[j] = lon[i];
+            la[j] = lat[i];
+            vin[j] = compute_valid ? (premask ? premask[i] : (uint8_t)0) : valid[i];
+            ex[j] = exclude ? exclude[i] : (uint8_t)0;
+        }
+    }
+    int last_cell = -1;  // probe cells are tens of km wide: a thread's points mostly share one
+    __shared__ int s_cells[64];
+    if (threadIdx.x < 64) s_cells[threadIdx.x] = -1;
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < BUILD_ITEMS; ++j) {
         const int64_t i = base + (int64_t)j * BUILD_TPB;
         if (i >= n) continue;
-        const T lo = lon[i], la = lat[i];
-        bool v;
-        if (compute_valid) {
-            v = valid_predicate<T>(lo, la, box, premask && premask[i]);
-            if (valid) valid[i] = v ? 1 : 0;
-        } else {
-            v = valid[i] != 0;
-        }
+        const bool v = compute_valid ? valid_predicate<T>(lo[j], la[j], box, vin[j] != 0) : vin[j] != 0;
+        if (compute_valid && valid) valid[i] = v ? 1 : 0;
         bool kept = false;
         if (v) {
             ++nv;
             first = min(first, (uint32_t)i);
-            bool skip = exclude && exclude[i];
+            bool skip = ex[j] != 0;
             if (!skip) {
                 float slo, clo, sla, cla;
-                __sincosf((float)lo * 0.017453292f, &slo, &clo);
-                __sincosf((float)la * 0.017453292f, &sla, &cla);
+                __sincosf((float)lo[j] * 0.017453292f, &slo, &clo);
+                __sincosf((float)la[j] * 0.017453292f, &sla, &cla);
                 const float fx = cla * clo, fy = cla * slo, fz = sla;
                 int face, iu, iv;
                 if (cover) {
@@ -248,7 +341,16 @@ __global__ void __launch_bounds__(BUILD_TPB)
                 }
                 if (!skip) {
                     face_cell_of(fx, fy, fz, OCC_G, face, iu, iv);
-                    occ[(face * OCC_G + iv) * OCC_G + iu] = 1;  // fire-and-forget; a warp's stores mostly coincide
+                    const int cell = (face * OCC_G + iv) * OCC_G + iu;
+                    if (cell != last_cell) {
+                        // every block sets the same few bytes, and a cache line that the whole grid writes is a
+                        // serial resource: announce each cell once per block (a race only costs a repeated store)
+                        if (s_cells[cell & 63] != cell) {
+                            s_cells[cell & 63] = cell;
+                            occ[cell] = 1;
+                        }
+                        last_cell = cell;
+                    }
                     kept = true;
                 }
             }
@@ -325,22 +427,35 @@ __device__ __forceinline__ int64_t table_key(const FaceTable &t, int face, int i
 }
 
 // Pass 2: exact ECEF coordinates of the kept points, their cell key and the histogram into table[key + 1].
+// tmp[i] = (x, y, z, cell key) - the record's source index is its position i, so the fourth word carries the key
+// to pass 3 (CELL_SKIP for points that are not indexed).
 template <typename T>
 __global__ void __launch_bounds__(BUILD_TPB)
     build_xyz_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, const uint8_t *__restrict__ keep,
-                     int G, const FaceTable ft, Rec<T> *__restrict__ tmp, uint32_t *__restrict__ cellid,
-                     uint32_t *__restrict__ table)
+                     int G, const FaceTable ft, Rec<T> *__restrict__ tmp, uint32_t *__restrict__ table)
 {
     const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * BUILD_ITEMS) + threadIdx.x;
+    T lo[BUILD_ITEMS], la[BUILD_ITEMS];
+    uint8_t kp[BUILD_ITEMS];
+#pragma unroll
+    for (int j = 0; j < BUILD_ITEMS; ++j) {
+        const int64_t i = base + (int64_t)j * BUILD_TPB;
+        lo[j] = la[j] = 0;
+        kp[j] = 0;
+        if (i < n) {
+            kp[j] = keep[i];
+            lo[j] = lon[i];
+            la[j] = lat[i];
+        }
+    }
 #pragma unroll
     for (int j = 0; j < BUILD_ITEMS; ++j) {
         const int64_t i = base + (int64_t)j * BUILD_TPB;
         if (i >= n) continue;
         uint32_t c = CELL_SKIP;
-        if (keep[i]) {
-            T x, y, z;
-            lonlat_to_xyz(lon[i], lat[i], x, y, z);
-            store_rec(tmp + i, x, y, z, (uint32_t)i);
+        T x = 0, y = 0, z = 0;
+        if (kp[j]) {
+            lonlat_to_xyz(lo[j], la[j], x, y, z);
             float fx, fy, fz;
             unit_f32<T>(x, y, z, fx, fy, fz);
             int face, iu, iv;
@@ -351,22 +466,33 @@ __global__ void __launch_bounds__(BUILD_TPB)
             c = (uint32_t)table_key(ft, face, iu, iv);
             atomicAdd(&table[c + 1], 1u);
         }
-        cellid[i] = c;
+        store_rec(tmp + i, x, y, z, c);
     }
 }
 
 // Pass 3: scatter.  table[c + 1] holds start(c) after the exclusive scan and ends as start(c + 1).
+constexpr int SCATTER_ITEMS = 4;
 template <typename T>
-__global__ void build_scatter_kernel(const Rec<T> *__restrict__ tmp, int64_t n, const uint32_t *__restrict__ cellid,
-                                     uint32_t *__restrict__ table, Rec<T> *__restrict__ recs)
+__global__ void __launch_bounds__(BUILD_TPB)
+    build_scatter_kernel(const Rec<T> *__restrict__ tmp, int64_t n, uint32_t *__restrict__ table,
+                         Rec<T> *__restrict__ recs)
 {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    uint32_t c = cellid[j];
-    if (c == CELL_SKIP) return;
-    uint32_t pos = atomicAdd(&table[c + 1], 1u);
-    Rec<T> r = load_rec(tmp + j);
-    store_rec(recs + pos, r.x, r.y, r.z, r.idx);
+    const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * SCATTER_ITEMS) + threadIdx.x;
+    Rec<T> r[SCATTER_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SCATTER_ITEMS; ++j) {
+        const int64_t i = base + (int64_t)j * BUILD_TPB;
+        r[j].idx = CELL_SKIP;
+        if (i < n) r[j] = load_rec(tmp + i);
+    }
+    uint32_t pos[SCATTER_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SCATTER_ITEMS; ++j)
+        if (r[j].idx != CELL_SKIP) pos[j] = atomicAdd(&table[r[j].idx + 1], 1u);
+#pragma unroll
+    for (int j = 0; j < SCATTER_ITEMS; ++j)
+        if (r[j].idx != CELL_SKIP)
+            store_rec(recs + pos[j], r[j].x, r[j].y, r[j].z, (uint32_t)(base + (int64_t)j * BUILD_TPB));
 }
 
 // Coarse table: number of points in each COARSE x COARSE block of fine cells, from the fine row prefix sums.
@@ -397,6 +523,7 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
 {
     (void)radius_hint;
     const int TPB = 256;
+    BuildTimer timer;
     int rc = ensure_pool_configured();
     if (rc != PRS_OK) return rc;
     ix->stream = st;
@@ -408,11 +535,15 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
     BoxT<T> bx;
     make_box(bx0, bx);
     const size_t occ_n = 6ull * OCC_G * OCC_G;
-    // scratch block: counters | rect[24] | occ[occ_n] | block_counts[n_blocks]
-    uint8_t *scratch = nullptr;
+    // workspace: counters | rect[24] | occ[occ_n] | block_counts[n_blocks] || unsorted records || keep flags
     const size_t off_counts = (256 + occ_n + 15) & ~(size_t)15;
-    const size_t scratch_bytes = off_counts + sizeof(uint2) * (size_t)n_blocks;
-    PRS_CK(cudaMallocAsync((void **)&scratch, scratch_bytes, st));
+    const size_t scratch_bytes = (off_counts + sizeof(uint2) * (size_t)n_blocks + 255) & ~(size_t)255;
+    const size_t tmp_bytes = (sizeof(Rec<T>) * (size_t)n + 255) & ~(size_t)255;
+    WorkspaceLease lease;
+    void *ws_base = nullptr;
+    rc = lease.acquire(scratch_bytes + tmp_bytes + (size_t)n, st, &ws_base);
+    if (rc != PRS_OK) return rc;
+    uint8_t *scratch = (uint8_t *)ws_base;
     PRS_CK(cudaMemsetAsync(scratch, 0, off_counts, st));
     BuildCounters *counters = (BuildCounters *)scratch;
     int *rect_dev = (int *)(scratch + 32);
@@ -433,17 +564,14 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
         PRS_CK(cudaMemcpyAsync(scratch, &init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
     // pass 1: validity, selection, occupancy probe (records are addressed by source index: no rank table needed)
-    Rec<T> *tmp = nullptr;
-    uint32_t *cellid = nullptr;
-    uint8_t *keep = nullptr;
-    PRS_CK(cudaMallocAsync((void **)&tmp, sizeof(Rec<T>) * (size_t)n, st));
-    PRS_CK(cudaMallocAsync((void **)&cellid, sizeof(uint32_t) * (size_t)n, st));
-    PRS_CK(cudaMallocAsync((void **)&keep, (size_t)n, st));
+    Rec<T> *tmp = (Rec<T> *)(scratch + scratch_bytes);
+    uint8_t *keep = scratch + scratch_bytes + tmp_bytes;
     build_select_kernel<T><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, valid, compute_valid, bx, premask, exclude,
                                                                      cover, keep, occ, counters, block_counts);
     PRS_CKL();
     build_reduce_kernel<<<96, TPB, 0, st>>>(occ, block_counts, n_blocks, rect_dev, counters);
     PRS_CKL();
+    timer.mark("pass 1 queued");
     // the one host round trip of the build: sizes the cell grid
     struct {
         BuildCounters c;
@@ -452,7 +580,7 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
     } h;
     rc = read_back_small(scratch, &h, sizeof(h), st);
     if (rc != PRS_OK) return rc;
-    PRS_CK(cudaFreeAsync(scratch, st));
+    timer.mark("counters read back");
     ix->n_valid = h.c.n_valid;
     ix->n_indexed = (int64_t)h.c.n_valid - (int64_t)h.c.n_skipped;
     ix->first_valid_source = h.c.first_source == 0xFFFFFFFFu ? 0u : h.c.first_source;
@@ -465,9 +593,6 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
         if (rc != PRS_OK) return rc;
     }
     if (ix->n_indexed <= 0) {
-        PRS_CK(cudaFreeAsync(tmp, st));
-        PRS_CK(cudaFreeAsync(cellid, st));
-        PRS_CK(cudaFreeAsync(keep, st));
         ix->n_indexed = 0;
         ix->G = COARSE;
         ix->Gc = 1;
@@ -526,31 +651,34 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
     ix->n_coarse = nc;
     if (nf >= 0xFFFFFFF0LL) return fail(PRS_ENOSUP, "cell table too large");
     // pass 2 + scan + pass 3
-    PRS_CK(cudaMallocAsync((void **)&ix->cell_start, sizeof(uint32_t) * (size_t)(nf + 1), st));
-    ix->bytes += sizeof(uint32_t) * (size_t)(nf + 1);
-    PRS_CK(cudaMemsetAsync(ix->cell_start, 0, sizeof(uint32_t) * (size_t)(nf + 1), st));
-    build_xyz_kernel<T><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, G, ix->fine, tmp, cellid, ix->cell_start);
+    // three leading pad words: cell_start + 1 (the array the scan walks) is then 16-byte aligned for 128-bit accesses
+    PRS_CK(cudaMallocAsync((void **)&ix->cell_alloc, sizeof(uint32_t) * (size_t)(nf + 4), st));
+    ix->cell_start = ix->cell_alloc + 3;
+    ix->bytes += sizeof(uint32_t) * (size_t)(nf + 4);
+    PRS_CK(cudaMemsetAsync(ix->cell_alloc, 0, sizeof(uint32_t) * (size_t)(nf + 4), st));
+    timer.mark("cell table allocated");
+    build_xyz_kernel<T><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, G, ix->fine, tmp, ix->cell_start);
     PRS_CKL();
     rc = scan_u32<uint32_t>(ix->cell_start + 1, ix->cell_start + 1, nf, 0, nullptr, st);
     if (rc != PRS_OK) return rc;
     size_t rec_bytes = sizeof(Rec<T>) * (size_t)ix->n_indexed;
     PRS_CK(cudaMallocAsync((void **)&ix->recs, rec_bytes, st));
+    timer.mark("records allocated");
     ix->bytes += rec_bytes;
-    build_scatter_kernel<T><<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, st>>>(tmp, n, cellid, ix->cell_start,
-                                                                             (Rec<T> *)ix->recs);
+    build_scatter_kernel<T><<<(unsigned)((n + BUILD_TPB * SCATTER_ITEMS - 1) / (BUILD_TPB * SCATTER_ITEMS)), BUILD_TPB, 0, st>>>(
+        tmp, n, ix->cell_start, (Rec<T> *)ix->recs);
     PRS_CKL();
     // coarse table
-    PRS_CK(cudaMallocAsync((void **)&ix->coarse_start, sizeof(uint32_t) * (size_t)(nc + 1), st));
-    ix->bytes += sizeof(uint32_t) * (size_t)(nc + 1);
+    PRS_CK(cudaMallocAsync((void **)&ix->coarse_alloc, sizeof(uint32_t) * (size_t)(nc + 4), st));
+    ix->coarse_start = ix->coarse_alloc + 3;
+    ix->bytes += sizeof(uint32_t) * (size_t)(nc + 4);
     PRS_CK(cudaMemsetAsync(ix->coarse_start, 0, sizeof(uint32_t), st));
     build_coarse_kernel<<<(unsigned)((nc + TPB - 1) / TPB), TPB, 0, st>>>(ix->cell_start, ix->fine, ix->coarse, nc,
                                                                          ix->coarse_start);
     PRS_CKL();
     rc = scan_u32<uint32_t>(ix->coarse_start + 1, ix->coarse_start + 1, nc, 1, nullptr, st);
     if (rc != PRS_OK) return rc;
-    PRS_CK(cudaFreeAsync(tmp, st));
-    PRS_CK(cudaFreeAsync(cellid, st));
-    PRS_CK(cudaFreeAsync(keep, st));
+    timer.mark("all queued");
     return PRS_OK;
 }
 

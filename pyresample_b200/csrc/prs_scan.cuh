@@ -16,13 +16,29 @@ template <typename In> __device__ __forceinline__ uint32_t scan_load(const In *i
     return i < n ? (uint32_t)(in[i] != 0 ? (sizeof(In) == 1 ? 1u : (uint32_t)in[i]) : 0u) : 0u;
 }
 
+// The SCAN_ITEMS consecutive items of a thread; 32-bit inputs at a 16-byte aligned address go as two 128-bit loads.
+template <typename In>
+__device__ __forceinline__ void scan_load_items(const In *in, int64_t base, int64_t n, uint32_t v[SCAN_ITEMS])
+{
+    if (sizeof(In) == 4 && base + SCAN_ITEMS <= n && (reinterpret_cast<uintptr_t>(in + base) & 15) == 0) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(in + base), b = *reinterpret_cast<const uint4 *>(in + base + 4);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = scan_load(in, base + j, n);
+}
+
 template <typename In> __global__ void scan_tile_sums(const In *__restrict__ in, int64_t n, uint32_t *__restrict__ sums)
 {
+    static_assert(SCAN_ITEMS == 8, "scan_load_items unpacks two uint4");
     __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    scan_load_items(in, base, n, v);
     uint32_t s = 0;
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) s += scan_load(in, base + j, n);
+    for (int j = 0; j < SCAN_ITEMS; ++j) s += v[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
@@ -42,12 +58,10 @@ __global__ void scan_tile_apply(const In *in, int64_t n, const uint32_t *__restr
     __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
+    scan_load_items(in, base, n, v);
     uint32_t s = 0;
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        v[j] = scan_load(in, base + j, n);
-        s += v[j];
-    }
+    for (int j = 0; j < SCAN_ITEMS; ++j) s += v[j];
     uint32_t incl = s;
     int lane = threadIdx.x & 31;
 #pragma unroll
@@ -60,10 +74,19 @@ __global__ void scan_tile_apply(const In *in, int64_t n, const uint32_t *__restr
     uint32_t woff = 0;
     for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_sums[w];
     uint32_t run = tile_offsets[blockIdx.x] + woff + (incl - s);
+    uint32_t o[SCAN_ITEMS];
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; ++j) {
-        if (base + j < n) out[base + j] = inclusive ? run + v[j] : run;
+        o[j] = inclusive ? run + v[j] : run;
         run += v[j];
+    }
+    if (base + SCAN_ITEMS <= n && (reinterpret_cast<uintptr_t>(out + base) & 15) == 0) {
+        *reinterpret_cast<uint4 *>(out + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(out + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j)
+            if (base + j < n) out[base + j] = o[j];
     }
 }
 

@@ -272,6 +272,123 @@ class AreaDefinition(BaseDefinition):
         return lons, lats
 
 
+class IncompatibleAreas(ValueError):
+    """Error when the areas to combine are not compatible (pyresample/geometry.py:66-67)."""
+
+
+def combine_area_extents_vertical(area1, area2):
+    """Extent of two areas stacked vertically (pyresample/geometry.py:2878-2896)."""
+    e1, e2 = area1.area_extent, area2.area_extent
+    if not (e1[0] == e2[0] and e1[2] == e2[2]):
+        raise IncompatibleAreas("Can't concatenate area definitions with incompatible area extents: "
+                                "{0} and {1}".format(area1, area2))
+    current_extent = list(e1)
+    if np.isclose(e1[1], e2[3]):
+        current_extent[1] = e2[1]
+    elif np.isclose(e1[3], e2[1]):
+        current_extent[3] = e2[3]
+    else:
+        raise IncompatibleAreas("Can't concatenate non-contiguous area definitions: "
+                                "{0} and {1}".format(area1, area2))
+    return current_extent
+
+
+def concatenate_area_defs(area1, area2, axis=0):
+    """Append *area2* to *area1* (pyresample/geometry.py:2899-2920); vertical only, like the reference."""
+    if axis != 0:
+        raise NotImplementedError('Only vertical contatenation is supported.')
+    if area1.proj_dict != area2.proj_dict or area1.width != area2.width:
+        raise IncompatibleAreas("Can't concatenate area definitions with different projections: "
+                                "{0} and {1}".format(area1, area2))
+    area_extent = combine_area_extents_vertical(area1, area2)
+    return AreaDefinition(area1.area_id, area1.description, area1.proj_id, area1.proj_dict, int(area1.width),
+                          int(area1.height + area2.height), area_extent, dtype=area1.dtype)
+
+
+class StackedAreaDefinition(BaseDefinition):
+    """Several vertically stacked AreaDefinitions (pyresample/geometry.py:2923-3049).
+
+    Contiguous members are merged on ``append`` like in the reference; ``get_lonlats`` stacks the members'
+    (GPU inverse-projected) coordinates.  For kd_tree it is a plain 2-D geometry: no reduce_data box (it is neither
+    Coordinate-, Grid- nor AreaDefinition, kd_tree.py:410-414).
+    """
+
+    def __init__(self, *definitions, **kwargs):
+        super().__init__(None, None, kwargs.get('nprocs', 1))
+        self.dtype = np.dtype(kwargs.get('dtype', np.float64))
+        self.defs = []
+        self.ndim = 2
+        for definition in definitions:
+            self.append(definition)
+
+    @property
+    def width(self):
+        return self.defs[0].width
+
+    @property
+    def height(self):
+        return sum(definition.height for definition in self.defs)
+
+    @property
+    def shape(self):
+        return (self.height, self.width)
+
+    @shape.setter
+    def shape(self, value):  # BaseDefinition.__init__ assigns it
+        pass
+
+    @property
+    def size(self):
+        return self.height * self.width
+
+    @size.setter
+    def size(self, value):
+        pass
+
+    @property
+    def proj_str(self):
+        return self.defs[0].proj_str
+
+    def append(self, definition):
+        if isinstance(definition, StackedAreaDefinition):
+            for area in definition.defs:
+                self.append(area)
+            return
+        if definition.height == 0:
+            return
+        if self.defs and self.defs[0].proj_dict != definition.proj_dict:
+            raise NotImplementedError('Cannot append areas: CRS mismatch')
+        try:
+            self.defs[-1] = concatenate_area_defs(self.defs[-1], definition)
+        except (IncompatibleAreas, IndexError):
+            self.defs.append(definition)
+
+    def get_lonlats(self, nprocs=None, data_slice=None, cache=False, dtype=None, chunks=None):
+        """Stack of the members' lon/lat arrays (pyresample/geometry.py:2966-2998)."""
+        llons, llats = [], []
+        try:
+            row_slice, col_slice = data_slice
+        except TypeError:
+            row_slice, col_slice = slice(0, self.height), slice(0, self.width)
+        if not isinstance(row_slice, slice):
+            raise TypeError("StackedAreaDefinition.get_lonlats takes row slices")
+        start = 0 if row_slice.start is None else row_slice.start
+        stop = self.height if row_slice.stop is None else row_slice.stop
+        offset = 0
+        for areadef in self.defs:
+            local = slice(max(start - offset, 0), min(max(stop - offset, 0), areadef.height), row_slice.step)
+            lons, lats = areadef.get_lonlats(nprocs=nprocs, data_slice=(local, col_slice), cache=cache, dtype=dtype)
+            llons.append(lons)
+            llats.append(lats)
+            offset += areadef.height
+        self.lons, self.lats = np.vstack(llons), np.vstack(llats)
+        return self.lons, self.lats
+
+    def squeeze(self):
+        """A single AreaDefinition if possible."""
+        return self.defs[0] if len(self.defs) == 1 else self
+
+
 def _yx_slice(data_slice):
     """AreaDefinition._get_yx_data_slice (pyresample/geometry.py:2491-2496)."""
     if data_slice is not None and isinstance(data_slice, slice):

@@ -17,6 +17,7 @@ fused entry points.  There is no CPU fallback: without the CUDA library and a GP
 from __future__ import annotations
 
 import ctypes
+import time
 import types
 import warnings
 from logging import getLogger
@@ -98,6 +99,7 @@ def _host(t):
 _PIPELINE_MIN_BYTES = 32 << 20
 _PIPELINE_MIN_RUN_BYTES = 4 << 20   # shorter runs of finished bands are not worth a copy of their own
 _side = {}
+_TIMELINE = None  # set to a list to collect host-side time stamps of the pipelined path (tools/timeline_e2e.py)
 
 
 def _side_streams():
@@ -138,6 +140,7 @@ def _nearest_pipelined(L, source, tg, n_t, host_rows, fill_row_host, radius):
     up, down = _side_streams()
     row_bytes = host_rows.shape[1]
     width, nrows = int(tg.grid.width), int(tg.nrows)
+    stamps = [("enter", time.perf_counter())] if _TIMELINE is not None else None
     up.wait_stream(main)
     with torch.cuda.stream(up):
         dev_data = _dev(host_rows)
@@ -153,6 +156,8 @@ def _nearest_pipelined(L, source, tg, n_t, host_rows, fill_row_host, radius):
                                             _ptr(out), _ptr(scratch), _ptr(band_live), _stream()))
     host_out = torch.empty((n_t, row_bytes), dtype=torch.uint8, pin_memory=True)
     runs = _band_runs(_host(band_live), _cabi.PRS_TILE_ROWS, nrows, width * row_bytes, _PIPELINE_MIN_RUN_BYTES)
+    if stamps is not None:
+        stamps.append(("fill stage done", time.perf_counter()))
     down.wait_stream(main)
     with torch.cuda.stream(down):
         for r0, r1, is_live in runs:
@@ -166,8 +171,16 @@ def _nearest_pipelined(L, source, tg, n_t, host_rows, fill_row_host, radius):
         for r0, r1, is_live in runs:
             if is_live:
                 host_out[r0 * width:r1 * width].copy_(out[r0 * width:r1 * width], non_blocking=True)
+    if stamps is not None:
+        stamps.append(("all work queued", time.perf_counter()))
+        data_ready.synchronize()
+        stamps.append(("data uploaded", time.perf_counter()))
     down.synchronize()
     main.synchronize()
+    if stamps is not None:
+        stamps.append(("done", time.perf_counter()))
+        _TIMELINE.append([(n, (t - stamps[0][1]) * 1e3) for n, t in stamps] +
+                         [("finished rows", sum(r1 - r0 for r0, r1, lv in runs if not lv)), ("rows", nrows)])
     return host_out.numpy()
 
 

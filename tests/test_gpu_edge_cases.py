@@ -201,3 +201,33 @@ def test_pipelined_nearest_equals_plain(kd, geometry, monkeypatch, min_run):
     masked = kd.resample_nearest(swath, data[:, 0], area, 30000, fill_value=None)
     want_m = kd_tree_ref.resample_nearest(swath, data[:, 0], area, 30000, fill_value=None)
     assert np.array_equal(masked.mask, want_m.mask) and np.array_equal(masked.filled(0), want_m.filled(0))
+
+
+def test_stacked_area_definition_as_target_and_source(kd, geometry):
+    """A StackedAreaDefinition behaves like the explicit lon/lat grid of its stacked members (geometry.py:2966-2998)."""
+    proj = "+proj=laea +lat_0=55 +lon_0=10 +a=6371228.0 +units=m"
+    top = geometry.AreaDefinition("t", "t", "t", proj, 120, 40, (-600000, 0, 600000, 400000))
+    far = geometry.AreaDefinition("f", "f", "f", proj, 120, 30, (-600000, -900000, 600000, -600000))
+    st = geometry.StackedAreaDefinition(top, far)
+    assert len(st.defs) == 2
+    lons, lats = st.get_lonlats()
+    want = [kd_tree_ref.get_lonlats(a) for a in (top, far)]
+    np.testing.assert_allclose(lons, np.vstack([w[0] for w in want]), rtol=0, atol=1e-9)
+    np.testing.assert_allclose(lats, np.vstack([w[1] for w in want]), rtol=0, atol=1e-9)
+    part = st.get_lonlats(data_slice=(slice(35, 50), slice(None)))
+    assert part[0].shape == (15, 120) and np.array_equal(part[0], lons[35:50])
+    rng = np.random.default_rng(58)
+    slon, slat = rng.uniform(-5, 25, 40000), rng.uniform(44, 60, 40000)
+    data = rng.normal(size=40000)
+    swath = geometry.SwathDefinition(slon, slat)
+    res = kd.resample_nearest(swath, data, st, 20000, fill_value=None)
+    grid = geometry.GridDefinition(np.vstack([w[0] for w in want]), np.vstack([w[1] for w in want]))
+    ref = kd_tree_ref.resample_nearest(swath, data, grid, 20000, fill_value=None)
+    assert res.shape == (70, 120)
+    assert np.array_equal(res.mask, ref.mask) and np.array_equal(res.filled(0), ref.filled(0))
+    # and as the source geometry (grid -> swath)
+    src_data = rng.normal(size=(70, 120))
+    tgt = geometry.SwathDefinition(rng.uniform(0, 20, 500), rng.uniform(48, 58, 500))
+    back = kd.resample_nearest(st, src_data, tgt, 20000, fill_value=-9)
+    ref_back = kd_tree_ref.resample_nearest(grid, src_data, tgt, 20000, fill_value=-9, reduce_data=False)
+    assert np.array_equal(back, ref_back)

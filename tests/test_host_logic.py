@@ -145,3 +145,28 @@ def test_band_runs_of_the_pipelined_path():
     assert runs == [(0, 24, False), (24, 56, True), (56, 77, False)]
     assert _band_runs(np.zeros(4, np.uint8), 8, 32, 10, 0) == [(0, 32, False)]
     assert _band_runs(np.ones(1, np.uint8), 8, 5, 10, 0) == [(0, 5, True)]
+
+
+def test_stacked_area_definition_append_rules():
+    """StackedAreaDefinition (pyresample/geometry.py:2923-2964): contiguous members merge, others stay apart."""
+    proj = "+proj=laea +lat_0=60 +lon_0=10 +a=6371228.0 +units=m"
+    top = geometry.AreaDefinition("t", "t", "t", proj, 100, 40, (-500000, 0, 500000, 400000))
+    mid = geometry.AreaDefinition("m", "m", "m", proj, 100, 30, (-500000, -300000, 500000, 0))
+    far = geometry.AreaDefinition("f", "f", "f", proj, 100, 20, (-500000, -900000, 500000, -700000))
+    st = geometry.StackedAreaDefinition(top, mid, far)
+    assert len(st.defs) == 2 and st.defs[0].height == 70 and st.defs[1].height == 20
+    assert st.defs[0].area_extent == (-500000, -300000, 500000, 400000)
+    assert st.shape == (90, 100) and st.size == 9000 and st.width == 100 and st.ndim == 2
+    assert geometry.StackedAreaDefinition(top, mid).squeeze() is not None
+    assert isinstance(geometry.StackedAreaDefinition(top, mid).squeeze(), geometry.AreaDefinition)
+    other = geometry.AreaDefinition("o", "o", "o", "+proj=eqc +datum=WGS84", 100, 20, (-500000, -900000, 500000, -700000))
+    with pytest.raises(NotImplementedError):
+        st.append(other)
+    narrow = geometry.AreaDefinition("n", "n", "n", proj, 50, 20, (-500000, -1300000, 0, -1100000))
+    with pytest.raises(geometry.IncompatibleAreas):
+        geometry.concatenate_area_defs(top, narrow)
+    with pytest.raises(geometry.IncompatibleAreas):
+        geometry.combine_area_extents_vertical(top, far)
+    import types
+    nested = geometry.StackedAreaDefinition(st, types.SimpleNamespace(height=0))  # empty members are dropped
+    assert len(nested.defs) == 2 and nested.height == 90

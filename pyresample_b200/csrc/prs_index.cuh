@@ -485,10 +485,19 @@ __global__ void __launch_bounds__(BUILD_TPB)
         r[j].idx = CELL_SKIP;
         if (i < n) r[j] = load_rec(tmp + i);
     }
+    // consecutive source points mostly share a cell: one atomic per (warp, cell) instead of one per point
+    const unsigned lane = threadIdx.x & 31u;
     uint32_t pos[SCATTER_ITEMS];
 #pragma unroll
-    for (int j = 0; j < SCATTER_ITEMS; ++j)
-        if (r[j].idx != CELL_SKIP) pos[j] = atomicAdd(&table[r[j].idx + 1], 1u);
+    for (int j = 0; j < SCATTER_ITEMS; ++j) {
+        const uint32_t c = r[j].idx;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        const unsigned leader = __ffs(peers) - 1;
+        uint32_t first = 0;
+        if (lane == leader && c != CELL_SKIP) first = atomicAdd(&table[c + 1], (uint32_t)__popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        pos[j] = first + __popc(peers & ((1u << lane) - 1u));
+    }
 #pragma unroll
     for (int j = 0; j < SCATTER_ITEMS; ++j)
         if (r[j].idx != CELL_SKIP)

@@ -330,7 +330,13 @@ def main():
                 if mode == "nearest":
                     return kd_tree.resample_nearest(src, host["data"].numpy(), area, radius)
                 return kd_tree.resample_gauss(src, host["data"].numpy(), area, radius, sigmas, neighbours=k)
-            # N > 1: rank 0 uploads, NCCL broadcast, every rank resamples and reads back its own row block
+            # N > 1: rank 0 uploads, NCCL broadcast, every rank resamples and reads back its own rows
+            if mode == "nearest" and "source_area" not in cfg:
+                # pipelined: coordinates first, the data follow while every rank builds its index and fills its rows
+                return distributed.resample_nearest_from_host(
+                    host["lon"].numpy() if rank == 0 else None, host["lat"].numpy() if rank == 0 else None,
+                    host["data"].numpy() if rank == 0 else None, area, radius, n_src, cfg["lon"].dtype,
+                    cfg["data"].dtype, channels)
             for n in names:
                 if rank == 0:
                     dev[n].copy_(host[n], non_blocking=True)
@@ -367,8 +373,10 @@ def main():
             e2e_ms = float(t.item())
         e2e = {"value": n_t_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "api": "pyresample_b200.kd_tree.resample_%s (numpy in, numpy out)" % ("nearest" if mode == "nearest"
-                                                                                     else "gauss")}
+               "api": ("pyresample_b200.kd_tree.resample_%s (numpy in, numpy out)" % mode) if world == 1 else
+                      ("pyresample_b200.distributed.resample_nearest_from_host (host arrays on rank 0 in, each rank's "
+                       "rows out to its host)" if mode == "nearest" and "source_area" not in cfg else
+                       "rank 0 uploads, NCCL broadcast, kd_tree resample of each rank's rows, read-back")}
 
     if rank == 0:
         peaks = {}

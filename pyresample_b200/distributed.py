@@ -138,6 +138,94 @@ def resample_nearest_sharded(source_geo_def, data, target_geo_def, radius_of_inf
     return out
 
 
+class _UploadAndBroadcast(object):
+    """Data arrival for kd_tree._nearest_pipelined on several ranks: ``src`` uploads the rows from its host memory on
+    the side stream, then they are broadcast (NCCL) - both while every rank classifies and fills its own rows."""
+
+    def __init__(self, host_rows, shape, src, group):
+        self.host_rows, self.shape, self.src, self.group = host_rows, tuple(shape), src, group
+        self.row_bytes = self.shape[1]
+
+    def start(self, main, up):
+        import torch
+        rank, _ = _world(self.group)
+        self.ready = None
+        if rank == self.src:
+            up.wait_stream(main)
+            with torch.cuda.stream(up):
+                self.dev = torch.from_numpy(self.host_rows).cuda(non_blocking=True)
+                self.ready = torch.cuda.Event()
+                self.ready.record(up)
+        else:
+            self.dev = torch.empty(self.shape, dtype=torch.uint8, device="cuda")
+
+    def finish(self, main):
+        import torch.distributed as dist
+        if self.ready is not None:
+            main.wait_event(self.ready)
+        dist.broadcast(self.dev, src=self.src, group=self.group)
+        return self.dev
+
+    def finish_without_start(self):
+        """For a rank that has nothing to resample but must take part in the broadcast."""
+        import torch
+        main = torch.cuda.current_stream()
+        self.start(main, main)
+        return self.finish(main)
+
+
+def resample_nearest_from_host(lons, lats, data, target_geo_def, radius_of_influence, n_source, coord_dtype,
+                               data_dtype, channels, fill_value=0, src=0, group=None, stripe=DEFAULT_STRIPE):
+    """Multi-rank ``resample_nearest`` whose source lives in the HOST memory of rank ``src``: ``lons``/``lats``
+    (``n_source`` points of ``coord_dtype``) and ``data`` (``(n_source[, channels])`` of ``data_dtype``) are numpy
+    arrays there and ``None`` on the other ranks, which only know the sizes and dtypes.
+
+    The coordinates are uploaded and broadcast first; every rank then builds its index and fills its rows while
+    the data follow (upload on ``src`` + broadcast), reads back the bands of rows that are already final, searches
+    the rest and reads it back: each rank returns its own rows ``(nrows, width[, channels])`` as a host array.
+    Same result as ``resample_nearest_sharded`` + a device-to-host copy.
+    """
+    import torch
+    import torch.distributed as dist
+    from . import _cabi, kd_tree
+    rank, world = _world(group)
+    target = geometry.as_geo_def(target_geo_def)
+    height = target.shape[0]
+    rows = shard_rows(height, world, rank) if stripe is None else cyclic_rows(height, world, rank, stripe)
+    coord_dtype, data_dtype = np.dtype(coord_dtype), np.dtype(data_dtype)
+    row_bytes = channels * data_dtype.itemsize
+    ll = torch.empty((2, n_source), dtype=getattr(torch, coord_dtype.name), device="cuda")
+    host_rows = None
+    if rank == src:
+        ll[0].copy_(torch.from_numpy(np.ascontiguousarray(lons, dtype=coord_dtype).ravel()), non_blocking=True)
+        ll[1].copy_(torch.from_numpy(np.ascontiguousarray(lats, dtype=coord_dtype).ravel()), non_blocking=True)
+        host_rows = kd_tree._byte_rows(np.ma.getdata(data))
+    if world > 1:
+        dist.broadcast(ll, src=src, group=group)
+    swath = geometry.SwathDefinition(ll[0], ll[1])
+    source = kd_tree._Source(swath, target, True, radius_of_influence, 1, need_ranks=False,
+                             cover_rows=rows if world > 1 else None)
+    fill_row_host = kd_tree._byte_rows(np.full((1, channels), fill_value, dtype=data_dtype))
+    tail = (channels,) if channels > 1 else ()
+    if source.index is None:  # no valid source point at all: every pixel is fill (kd_tree.py:336-341)
+        if world > 1:  # stay in step with the collective of the other ranks
+            _UploadAndBroadcast(host_rows, (n_source, row_bytes), src, group).finish_without_start()
+        return np.full((rows[1], target.shape[1]) + tail, fill_value, dtype=data_dtype)
+    tg, n_t, keep = kd_tree._make_target(source, target, True, radius_of_influence, rows=rows)
+    if n_t == 0:
+        if world > 1:
+            _UploadAndBroadcast(host_rows, (n_source, row_bytes), src, group).finish_without_start()
+        return np.empty((0, target.shape[1]) + tail, dtype=data_dtype)
+    arrival = _UploadAndBroadcast(host_rows, (n_source, row_bytes), src, group) if world > 1 \
+        else kd_tree._HostUpload(host_rows)
+    L = _cabi.lib()
+    res = kd_tree._nearest_pipelined(L, source, tg, n_t, arrival, fill_row_host, radius_of_influence)
+    del keep
+    res = res.view(data_dtype)
+    nrows = n_t // target.shape[1]
+    return res.reshape((nrows, target.shape[1]) + tail)
+
+
 def concat_row_blocks(blocks):
     """Host-side concatenation of contiguous per-rank row blocks."""
     return np.concatenate(blocks, axis=0)

@@ -127,25 +127,43 @@ def _band_runs(live, band_rows, nrows, row_bytes_total, min_run_bytes):
     return [(int(b0) * band_rows, int(min(b1 * band_rows, nrows)), bool(live[b0])) for b0, b1 in zip(starts, ends)]
 
 
-def _nearest_pipelined(L, source, tg, n_t, host_rows, fill_row_host, radius):
+class _HostUpload(object):
+    """Arrival of the source rows on the device for _nearest_pipelined: upload from host memory on a side stream."""
+
+    def __init__(self, host_rows):
+        self.host_rows = host_rows
+        self.row_bytes = host_rows.shape[1]
+
+    def start(self, main, up):
+        torch = _torch()
+        up.wait_stream(main)
+        with torch.cuda.stream(up):
+            self.dev = _dev(self.host_rows)
+            self.ready = torch.cuda.Event()
+            self.ready.record(up)
+
+    def finish(self, main):
+        """Make ``main`` wait for the rows; returns the device tensor."""
+        main.wait_event(self.ready)
+        return self.dev
+
+
+def _nearest_pipelined(L, source, tg, n_t, arrival, fill_row_host, radius):
     """resample_nearest for host arrays with the PCIe transfers overlapped (both directions at once).
 
-    The result of every tile that cannot have a neighbour is the fill value whatever the data are, so: upload the
-    data on a side stream; meanwhile classify + fill (prs_resample_nearest_fill) and start reading back the bands
-    of rows that are already final; when the data have arrived, search the remaining tiles
+    The result of every tile that cannot have a neighbour is the fill value whatever the data are, so: start the
+    arrival of the data (``arrival.start``: an upload on a side stream; pyresample_b200/distributed.py adds a
+    broadcast); meanwhile classify + fill (prs_resample_nearest_fill) and start reading back the bands of rows
+    that are already final; when the data have arrived (``arrival.finish``), search the remaining tiles
     (prs_resample_nearest_search) and read back the other bands.  Output identical to prs_resample_nearest.
     """
     torch = _torch()
     main = torch.cuda.current_stream()
     up, down = _side_streams()
-    row_bytes = host_rows.shape[1]
+    row_bytes = arrival.row_bytes
     width, nrows = int(tg.grid.width), int(tg.nrows)
     stamps = [("enter", time.perf_counter())] if _TIMELINE is not None else None
-    up.wait_stream(main)
-    with torch.cuda.stream(up):
-        dev_data = _dev(host_rows)
-        data_ready = torch.cuda.Event()
-        data_ready.record(up)
+    arrival.start(main, up)
     fill_row = _dev(fill_row_host)
     out = torch.empty((n_t, row_bytes), dtype=torch.uint8, device="cuda")
     scratch = torch.empty(int(L.prs_resample_scratch_bytes(ctypes.byref(tg))), dtype=torch.uint8, device="cuda")
@@ -163,7 +181,7 @@ def _nearest_pipelined(L, source, tg, n_t, host_rows, fill_row_host, radius):
         for r0, r1, is_live in runs:
             if not is_live:
                 host_out[r0 * width:r1 * width].copy_(out[r0 * width:r1 * width], non_blocking=True)
-    main.wait_event(data_ready)
+    dev_data = arrival.finish(main)
     _cabi.check(L.prs_resample_nearest_search(handle, ctypes.byref(tg), float(radius), _ptr(dev_data), row_bytes,
                                               _ptr(fill_row), _ptr(out), _ptr(scratch), _stream()))
     down.wait_stream(main)
@@ -173,8 +191,6 @@ def _nearest_pipelined(L, source, tg, n_t, host_rows, fill_row_host, radius):
                 host_out[r0 * width:r1 * width].copy_(out[r0 * width:r1 * width], non_blocking=True)
     if stamps is not None:
         stamps.append(("all work queued", time.perf_counter()))
-        data_ready.synchronize()
-        stamps.append(("data uploaded", time.perf_counter()))
     down.synchronize()
     main.synchronize()
     if stamps is not None:
@@ -1035,7 +1051,7 @@ def _resample(source_geo_def, data, target_geo_def, resample_type,
         row_bytes = host_rows.shape[1]
         fill_row_host = _byte_rows(np.full((1, channels), fill_value, dtype=new_data.dtype))
         if tg.kind == PRS_TARGET_AREA and n_t * row_bytes >= _PIPELINE_MIN_BYTES:
-            result = _nearest_pipelined(L, source, tg, n_t, host_rows, fill_row_host,
+            result = _nearest_pipelined(L, source, tg, n_t, _HostUpload(host_rows), fill_row_host,
                                         radius_of_influence).view(new_data.dtype)
         else:
             dev_data = _dev(host_rows)

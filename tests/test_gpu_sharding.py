@@ -56,3 +56,19 @@ def test_cyclic_row_plan():
             g = distributed.cyclic_global_rows(h, w, r, s)
             local = np.arange(nrows)
             assert np.array_equal(row0 + (local // blk) * stride + local % blk, g)
+
+
+def test_resample_nearest_from_host_single_rank(cuda_lib):
+    """The pipelined multi-rank entry point, run on one rank, equals the plain numpy API."""
+    from pyresample_b200 import distributed, geometry, kd_tree
+    rng = np.random.default_rng(71)
+    lon = rng.uniform(-30, 30, 90000).astype(np.float32)
+    lat = rng.uniform(-20, 35, 90000).astype(np.float32)
+    data = rng.normal(size=(90000, 2)).astype(np.float32)
+    area = geometry.AreaDefinition("g", "g", "g", "+proj=eqc +datum=WGS84", 900, 500,
+                                   (-10018754.17, -6000000.0, 10018754.17, 7000000.0))
+    got = distributed.resample_nearest_from_host(lon, lat, data, area, 40000, lon.size, lon.dtype, data.dtype, 2,
+                                                 fill_value=-1)
+    want = kd_tree.resample_nearest(geometry.SwathDefinition(lon, lat), data, area, 40000, fill_value=-1)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert (want != -1).any()

@@ -422,8 +422,12 @@ def inverse(projection, x, y):
     y = np.asarray(y, dtype=np.float64)
     pm = _f(d, "pm", 0.0) or 0.0
     if name in ("longlat", "latlong", "lonlat", "latlon"):
-        # geographic CRS -> its own geodetic CRS: identity (plus prime-meridian shift back to Greenwich)
-        return x + pm, y * 1.0
+        # geographic CRS -> its own geodetic CRS: identity (plus prime-meridian shift back to Greenwich, wrapped
+        # into [-180, 180] like PROJ's adjlon; pinned by test_resamplers/test_nearest.py:130-143, sum 115591.0)
+        lon = x + pm
+        if pm != 0.0 and not d.get("over"):
+            lon = np.where(lon > 180.0, lon - 360.0, np.where(lon < -180.0, lon + 360.0, lon))
+        return lon, y * 1.0
     to_meter = _f(d, "to_meter", None)
     if to_meter is None:
         to_meter = _UNITS[str(d.get("units", "m"))]

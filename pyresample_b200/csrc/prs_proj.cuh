@@ -245,6 +245,8 @@ __device__ inline void proj_inverse(const prs_proj_params &P, double x, double y
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     if (P.kind == PRS_PROJ_LONGLAT) {
         lon = x + P.pm_deg;
+        // a prime-meridian shift is wrapped back into [-180, 180] (PROJ's adjlon; test_resamplers/test_nearest.py:130-143)
+        if (P.pm_deg != 0.0 && !P.over) lon = lon > 180.0 ? lon - 360.0 : (lon < -180.0 ? lon + 360.0 : lon);
         lat = y;
         return;
     }

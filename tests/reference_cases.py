@@ -309,3 +309,52 @@ def case_errors(kd):
 
 ALL_CASES = [case_base_scalars, case_nearest_cross_sums, case_nearest_masked_swath_target, case_nearest_1d_and_empty,
              case_gauss_and_custom, case_masked_and_fill, case_from_sample_dtypes, case_ssmis_self_map, case_errors]
+
+
+# --------------------------------------------------------------- KDTreeNearestXarrayResampler
+def nearest_resampler_fixtures(geometry):
+    """The geometries and arrays of pyresample/test/conftest.py:31-34,118-135,204-340 as plain numpy objects."""
+    def test_longitude(start, stop, shape, dtype=np.float32):
+        if start > 0 > stop:
+            stop += 360.0
+        row = np.linspace(start, stop, num=shape[1]).astype(dtype)
+        arr = np.repeat([row], shape[0], axis=0)
+        if stop > 360.0:
+            arr[arr > 360.0] -= 360
+        return arr
+
+    def test_latitude(start, stop, shape, dtype=np.float32):
+        col = np.linspace(start, stop, num=shape[0]).astype(dtype).reshape((shape[0], 1))
+        return np.repeat(col, shape[1], axis=1)
+
+    shape = (50, 10)
+    fx = {}
+    fx["euro_lonlats"] = (test_longitude(3.0, 12.0, shape), test_latitude(75.0, 26.0, shape))
+    alons = test_longitude(172.0, 190.0, shape)
+    alons[alons > 180.0] -= 360.0
+    fx["antimeridian_lonlats"] = (alons, test_latitude(25.0, 33.0, shape))
+    stere = dict(a='6378144.0', b='6356759.0', proj='stere')
+    extent = (-1370912.72, -909968.64000000001, 1029087.28, 1490031.3600000001)
+    fx["area_stere_source"] = geometry.AreaDefinition("s", "s", "s", dict(stere, lat_0='52.00', lat_ts='52.00', lon_0='5.00'),
+                                                      10, 50, extent)
+    fx["area_stere_target"] = geometry.AreaDefinition("t", "t", "t", dict(stere, lat_0='50.00', lat_ts='50.00', lon_0='8.00'),
+                                                      85, 80, extent)
+    fx["area_lonlat_pm180_target"] = geometry.AreaDefinition(
+        "p", "p", "p", {'proj': 'longlat', 'pm': '180.0', 'datum': 'WGS84', 'no_defs': None}, 85, 80,
+        (-20.0, 20.0, 20.0, 35.0))
+    fx["coord_def_2d_float32"] = (
+        np.array([[11.5, 12.562036, 12.9]] * 4, dtype=np.float32),
+        np.array([[55.715613, 55.715613, 55.715613], [55.715613, 55.715613, 55.715613],
+                  [55.715613, np.nan, 55.715613], [55.715613, 55.715613, 55.715613]], dtype=np.float32))
+    fx["swath_1d"] = (np.array([11.280789, 12.649354, 12.080402]), np.array([56.011037, 55.629675, 55.641535]))
+    fx["data_1d"] = np.array([1., 2., 3.], dtype=np.float32)
+    fx["data_2d"] = np.fromfunction(lambda y, x: y * x, shape, dtype=np.float32)
+    fx["data_3d"] = np.fromfunction(lambda y, x, b: y * x * b, (50, 10, 3), dtype=np.float32)
+    return fx
+
+
+NEAREST_RESAMPLER_SUMS = {  # test_resamplers/test_nearest.py:96-228
+    "swath_2d_to_area": 167913.0, "area_to_area": 303048.0, "swath_pm180": 115591.0, "area_no_roi": 952386.0,
+    "area_no_roi_no_geocentric": 20666.0, "area_3d": 909144.0}
+NEAREST_1D_EXPECTED = np.array([[1., 2., 2.], [1., 2., 2.], [1., np.nan, 2.], [1., 2., 2.]])  # :67-72
+NEAREST_1D_INT_EXPECTED = np.array([[1, 2, 2], [1, 2, 2], [1, 255, 2], [1, 2, 2]])           # :88-93

@@ -82,3 +82,37 @@ def test_kdtree_ref_against_c_brute_force(dtype, k):
     # pykdtree call contract (future/resamplers test_nearest.py:311-373): missing -> n / inf, mask skips points
     d, i = KDTreeRef(src).query(qry[:5] * 2, k=1, distance_upper_bound=10.0)
     assert (i == 6000).all() and np.isinf(d).all()
+
+
+def test_nearest_resampler_restatement_matches_reference_literals():
+    """oracle/nearest_ref.py against test_resamplers/test_nearest.py:55-228 (KDTreeNearestXarrayResampler)."""
+    from oracle import nearest_ref
+    from pyresample_b200 import geometry
+    import reference_cases as rc
+    fx = rc.nearest_resampler_fixtures(geometry)
+    swath_1d = geometry.SwathDefinition(*fx["swath_1d"])
+    grid = geometry.CoordinateDefinition(*fx["coord_def_2d_float32"])
+    res = nearest_ref.resample(swath_1d, grid, fx["data_1d"], (0,), mask=np.isnan(fx["data_1d"]),
+                               radius_of_influence=100000)
+    np.testing.assert_allclose(res, rc.NEAREST_1D_EXPECTED)
+    res = nearest_ref.resample(swath_1d, grid, np.array([1, 2, 3]), (0,), fill_value=255, radius_of_influence=100000)
+    np.testing.assert_equal(res, rc.NEAREST_1D_INT_EXPECTED)
+    euro = geometry.SwathDefinition(*fx["euro_lonlats"])
+    anti = geometry.SwathDefinition(*fx["antimeridian_lonlats"])
+    src, tgt, pm = fx["area_stere_source"], fx["area_stere_target"], fx["area_lonlat_pm180_target"]
+    d2, d3 = fx["data_2d"], fx["data_3d"]
+    S = rc.NEAREST_RESAMPLER_SUMS
+    mask = nearest_ref.compute_data_mask(d2, (0, 1))
+    assert float(np.nansum(nearest_ref.resample(euro, tgt, d2, (0, 1), mask=mask, radius_of_influence=50000))) \
+        == S["swath_2d_to_area"]
+    assert float(np.nansum(nearest_ref.resample(src, tgt, d2, (0, 1), radius_of_influence=50000))) == S["area_to_area"]
+    assert float(np.nansum(nearest_ref.resample(anti, pm, d2, (0, 1), mask=mask, radius_of_influence=50000))) \
+        == S["swath_pm180"]
+    res = nearest_ref.resample(src, tgt, d2, (0, 1))
+    assert res.shape == (80, 85) and float(np.nansum(res)) == S["area_no_roi"]
+    radius = nearest_ref.compute_radius_of_influence(src, tgt, fail_source=True, fail_target=True)
+    assert radius == 10000
+    assert float(np.nansum(nearest_ref.resample(src, tgt, d2, (0, 1), radius_of_influence=radius))) \
+        == S["area_no_roi_no_geocentric"]
+    res3 = nearest_ref.resample(src, tgt, d3, (0, 1), radius_of_influence=50000)
+    assert res3.shape == (80, 85, 3) and float(np.nansum(res3)) == S["area_3d"]

@@ -358,3 +358,24 @@ NEAREST_RESAMPLER_SUMS = {  # test_resamplers/test_nearest.py:96-228
     "area_no_roi_no_geocentric": 20666.0, "area_3d": 909144.0}
 NEAREST_1D_EXPECTED = np.array([[1., 2., 2.], [1., 2., 2.], [1., np.nan, 2.], [1., 2., 2.]])  # :67-72
 NEAREST_1D_INT_EXPECTED = np.array([[1, 2, 2], [1, 2, 2], [1, 255, 2], [1, 2, 2]])           # :88-93
+
+
+# --------------------------------------------------------------- image containers / linesamples
+def image_fixtures(geometry):
+    """pyresample/test/test_image.py:32-75."""
+    area_def = geometry.AreaDefinition('areaD', 'Europe (3km, HRV, VTC)', 'areaD',
+                                       {'a': '6378144.0', 'b': '6356759.0', 'lat_0': '50.00', 'lat_ts': '50.00',
+                                        'lon_0': '8.00', 'proj': 'stere'}, 800, 800,
+                                       [-1370912.72, -909968.64000000001, 1029087.28, 1490031.3600000001])
+
+    def msg(n):
+        return geometry.AreaDefinition('msg_full', 'Full globe MSG image 0 degrees', 'msg_full',
+                                       {'a': '6378169.0', 'b': '6356584.0', 'h': '35785831.0', 'lon_0': '0',
+                                        'proj': 'geos'}, n, n,
+                                       [-5568742.4000000004, -5568742.4000000004, 5568742.4000000004,
+                                        5568742.4000000004])
+    return area_def, msg(3712), msg(928)
+
+
+IMAGE_NEAREST_SUM = 399936.70287099993        # test_image.py:130-138
+IMAGE_NEAREST_RESIZE_SUM = 2212023.0175830    # test_image.py:140-148

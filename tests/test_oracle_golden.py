@@ -116,3 +116,15 @@ def test_nearest_resampler_restatement_matches_reference_literals():
         == S["area_no_roi_no_geocentric"]
     res3 = nearest_ref.resample(src, tgt, d3, (0, 1), radius_of_influence=50000)
     assert res3.shape == (80, 85, 3) and float(np.nansum(res3)) == S["area_3d"]
+
+
+def test_image_container_literals_pin_the_geos_source_path():
+    """test_image.py:130-148: full-disk geos 3712x3712 source (off-earth pixels are inf) -> stere / geos targets."""
+    from pyresample_b200 import geometry
+    import reference_cases as rc
+    area_def, msg_area, msg_resize = rc.image_fixtures(geometry)
+    data = np.fromfunction(lambda y, x: y * x * 10 ** -6, (3712, 3712))
+    res = kd_tree_ref.resample_nearest(msg_area, data.ravel(), area_def, 50000, segments=1)
+    assert abs(res.sum() - rc.IMAGE_NEAREST_SUM) < 5e-8
+    res = kd_tree_ref.resample_nearest(msg_area, data.ravel(), msg_resize, 50000, segments=1)
+    assert abs(res.sum() - rc.IMAGE_NEAREST_RESIZE_SUM) < 5e-8

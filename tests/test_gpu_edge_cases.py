@@ -231,3 +231,31 @@ def test_stacked_area_definition_as_target_and_source(kd, geometry):
     back = kd.resample_nearest(st, src_data, tgt, 20000, fill_value=-9)
     ref_back = kd_tree_ref.resample_nearest(grid, src_data, tgt, 20000, fill_value=-9, reduce_data=False)
     assert np.array_equal(back, ref_back)
+
+
+def test_device_neighbour_info_matches_get_sample(kd, geometry, tmp_path):
+    """Neighbour info saved, reloaded and kept in HBM samples exactly like get_sample_from_neighbour_info."""
+    from pyresample_b200 import neighbour_cache as nc
+    rng = np.random.default_rng(59)
+    lon, lat = rng.uniform(0, 20, 30000), rng.uniform(40, 60, 30000)
+    lon[::50] = np.nan
+    swath = geometry.SwathDefinition(lon, lat)
+    area = geometry.AreaDefinition("a", "a", "a", "+proj=laea +lat_0=50 +lon_0=10 +a=6371228.0 +units=m", 300, 200,
+                                   (-900000, -700000, 900000, 700000))
+    info = kd.get_neighbour_info(swath, area, 30000, neighbours=1)
+    path = tmp_path / "n.npz"
+    nc.save_neighbour_info(path, *info)
+    loaded = nc.load_neighbour_info(path)
+    for a, b in zip(info, loaded):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+    dev = nc.DeviceNeighbourInfo.load(path)
+    for data in (rng.normal(size=30000), rng.normal(size=(30000, 3)).astype(np.float32),
+                 rng.integers(0, 200, 30000).astype(np.uint8)):
+        for fill in (0, None):
+            want = kd.get_sample_from_neighbour_info('nn', area.shape, data, *info[:3], fill_value=fill)
+            got = dev.sample_nearest(data, area.shape, fill_value=fill)
+            assert got.dtype == want.dtype and got.shape == want.shape
+            assert np.array_equal(np.ma.getmaskarray(got), np.ma.getmaskarray(want))
+            assert np.array_equal(np.ma.getdata(got), np.ma.getdata(want))
+    ref = kd_tree_ref.resample_nearest(swath, np.arange(30000.), area, 30000, fill_value=-1)
+    assert np.array_equal(dev.sample_nearest(np.arange(30000.), area.shape, fill_value=-1), ref)

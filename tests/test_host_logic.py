@@ -170,3 +170,21 @@ def test_stacked_area_definition_append_rules():
     import types
     nested = geometry.StackedAreaDefinition(st, types.SimpleNamespace(height=0))  # empty members are dropped
     assert len(nested.defs) == 2 and nested.height == 90
+
+
+def test_neighbour_info_file_round_trip(tmp_path):
+    """save/load keeps masks, dtypes and shapes - also the empty-info form (int32 indices, distances 1.0)."""
+    from pyresample_b200 import neighbour_cache as nc
+    rng = np.random.default_rng(3)
+    vii = rng.random(1003) < 0.7
+    voi = rng.random((17, 13)) < 0.9
+    ia = rng.integers(0, vii.sum() + 1, size=(int(voi.sum()), 4)).astype(np.uint32)
+    da = rng.random((int(voi.sum()), 4)).astype(np.float32)
+    path = tmp_path / "info.npz"
+    nc.save_neighbour_info(path, vii, voi, ia, da)
+    v1, v2, i2, d2 = nc.load_neighbour_info(path)
+    assert v1.dtype == bool and np.array_equal(v1, vii) and v2.shape == (17, 13) and np.array_equal(v2, voi)
+    assert i2.dtype == np.uint32 and np.array_equal(i2, ia) and d2.dtype == np.float32 and np.array_equal(d2, da)
+    nc.save_neighbour_info(path, np.zeros(5, bool), np.ones(6, bool), np.full(6, 5, np.int32), None)
+    v1, v2, i2, d2 = nc.load_neighbour_info(path)
+    assert not v1.any() and v2.all() and i2.dtype == np.int32 and d2 is None

@@ -428,8 +428,10 @@ __device__ __forceinline__ int64_t table_key(const FaceTable &t, int face, int i
 
 // Pass 2: exact ECEF coordinates of the kept points, their cell key and the histogram into table[key + 1].
 // tmp[i] = (x, y, z, cell key) - the record's source index is its position i, so the fourth word carries the key
-// to pass 3 (CELL_SKIP for points that are not indexed).
-template <typename T>
+// to pass 3.  Points that are not kept are not written.
+// SPARSE (a rank of a sharded run keeps a fraction of the points): the coordinates are only loaded for kept points;
+// otherwise all loads are issued up front.
+template <typename T, bool SPARSE>
 __global__ void __launch_bounds__(BUILD_TPB)
     build_xyz_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, const uint8_t *__restrict__ keep,
                      int G, const FaceTable ft, Rec<T> *__restrict__ tmp, uint32_t *__restrict__ table)
@@ -440,10 +442,13 @@ __global__ void __launch_bounds__(BUILD_TPB)
 #pragma unroll
     for (int j = 0; j < BUILD_ITEMS; ++j) {
         const int64_t i = base + (int64_t)j * BUILD_TPB;
+        kp[j] = i < n ? keep[i] : (uint8_t)0;
+    }
+#pragma unroll
+    for (int j = 0; j < BUILD_ITEMS; ++j) {
+        const int64_t i = base + (int64_t)j * BUILD_TPB;
         lo[j] = la[j] = 0;
-        kp[j] = 0;
-        if (i < n) {
-            kp[j] = keep[i];
+        if (i < n && (!SPARSE || kp[j])) {
             lo[j] = lon[i];
             la[j] = lat[i];
         }
@@ -451,21 +456,18 @@ __global__ void __launch_bounds__(BUILD_TPB)
 #pragma unroll
     for (int j = 0; j < BUILD_ITEMS; ++j) {
         const int64_t i = base + (int64_t)j * BUILD_TPB;
-        if (i >= n) continue;
-        uint32_t c = CELL_SKIP;
-        T x = 0, y = 0, z = 0;
-        if (kp[j]) {
-            lonlat_to_xyz(lo[j], la[j], x, y, z);
-            float fx, fy, fz;
-            unit_f32<T>(x, y, z, fx, fy, fz);
-            int face, iu, iv;
-            face_cell_of(fx, fy, fz, G, face, iu, iv);
-            // the table rectangle is a superset of the probe cells by construction; clamp defensively
-            iu = min(max(iu, ft.fu0[face]), ft.fu0[face] + ft.fw[face] - 1);
-            iv = min(max(iv, ft.fv0[face]), ft.fv0[face] + ft.fh[face] - 1);
-            c = (uint32_t)table_key(ft, face, iu, iv);
-            atomicAdd(&table[c + 1], 1u);
-        }
+        if (!kp[j]) continue;
+        T x, y, z;
+        lonlat_to_xyz(lo[j], la[j], x, y, z);
+        float fx, fy, fz;
+        unit_f32<T>(x, y, z, fx, fy, fz);
+        int face, iu, iv;
+        face_cell_of(fx, fy, fz, G, face, iu, iv);
+        // the table rectangle is a superset of the probe cells by construction; clamp defensively
+        iu = min(max(iu, ft.fu0[face]), ft.fu0[face] + ft.fw[face] - 1);
+        iv = min(max(iv, ft.fv0[face]), ft.fv0[face] + ft.fh[face] - 1);
+        const uint32_t c = (uint32_t)table_key(ft, face, iu, iv);
+        atomicAdd(&table[c + 1], 1u);
         store_rec(tmp + i, x, y, z, c);
     }
 }
@@ -474,16 +476,21 @@ __global__ void __launch_bounds__(BUILD_TPB)
 constexpr int SCATTER_ITEMS = 4;
 template <typename T>
 __global__ void __launch_bounds__(BUILD_TPB)
-    build_scatter_kernel(const Rec<T> *__restrict__ tmp, int64_t n, uint32_t *__restrict__ table,
-                         Rec<T> *__restrict__ recs)
+    build_scatter_kernel(const Rec<T> *__restrict__ tmp, const uint8_t *__restrict__ keep, int64_t n,
+                         uint32_t *__restrict__ table, Rec<T> *__restrict__ recs)
 {
     const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * SCATTER_ITEMS) + threadIdx.x;
     Rec<T> r[SCATTER_ITEMS];
+    uint8_t kp[SCATTER_ITEMS];
 #pragma unroll
     for (int j = 0; j < SCATTER_ITEMS; ++j) {
         const int64_t i = base + (int64_t)j * BUILD_TPB;
+        kp[j] = i < n ? keep[i] : (uint8_t)0;
+    }
+#pragma unroll
+    for (int j = 0; j < SCATTER_ITEMS; ++j) {
         r[j].idx = CELL_SKIP;
-        if (i < n) r[j] = load_rec(tmp + i);
+        if (kp[j]) r[j] = load_rec(tmp + base + (int64_t)j * BUILD_TPB);
     }
     // consecutive source points mostly share a cell: one atomic per (warp, cell) instead of one per point
     const unsigned lane = threadIdx.x & 31u;
@@ -666,7 +673,10 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
     ix->bytes += sizeof(uint32_t) * (size_t)(nf + 4);
     PRS_CK(cudaMemsetAsync(ix->cell_alloc, 0, sizeof(uint32_t) * (size_t)(nf + 4), st));
     timer.mark("cell table allocated");
-    build_xyz_kernel<T><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, G, ix->fine, tmp, ix->cell_start);
+    if (ix->n_indexed * 2 < n)  // a sharded rank (or a heavily masked source): most points are skipped
+        build_xyz_kernel<T, true><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, G, ix->fine, tmp, ix->cell_start);
+    else
+        build_xyz_kernel<T, false><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, G, ix->fine, tmp, ix->cell_start);
     PRS_CKL();
     rc = scan_u32<uint32_t>(ix->cell_start + 1, ix->cell_start + 1, nf, 0, nullptr, st);
     if (rc != PRS_OK) return rc;
@@ -675,7 +685,7 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
     timer.mark("records allocated");
     ix->bytes += rec_bytes;
     build_scatter_kernel<T><<<(unsigned)((n + BUILD_TPB * SCATTER_ITEMS - 1) / (BUILD_TPB * SCATTER_ITEMS)), BUILD_TPB, 0, st>>>(
-        tmp, n, ix->cell_start, (Rec<T> *)ix->recs);
+        tmp, keep, n, ix->cell_start, (Rec<T> *)ix->recs);
     PRS_CKL();
     // coarse table
     PRS_CK(cudaMallocAsync((void **)&ix->coarse_alloc, sizeof(uint32_t) * (size_t)(nc + 4), st));

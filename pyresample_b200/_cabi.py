@@ -76,8 +76,9 @@ _QUERY_INSTANCES = [(t, k) for t in ("float", "double") for k in (1, 4, 8, 16, 3
 def build(force=False, verbose=False, jobs=None):
     """Compile the CUDA library for sm_100a into ``pyresample_b200/libprs_b200.so``.
 
-    ``prs_b200.cu`` holds the C-ABI and the small kernels; the query kernels are instantiated once per
-    (tree dtype, K) in ``prs_query_inst.cu`` - the translation units are compiled in parallel and linked.
+    ``prs_b200.cu`` holds the C-ABI and the small kernels; the query kernels are instantiated per (tree dtype, K)
+    - and per target kind for K >= 16 - in ``prs_query_inst.cu``; the translation units are compiled in parallel
+    and linked.
     """
     if not force and not needs_rebuild():
         return _SO_PATH
@@ -94,8 +95,15 @@ def build(force=False, verbose=False, jobs=None):
         flags.append("-Xptxas=-v")
     units = [(os.path.join(_SRC_DIR, "prs_b200.cu"), os.path.join(obj_dir, "prs_b200.o"), [])]
     for t, k in _QUERY_INSTANCES:
-        units.append((os.path.join(_SRC_DIR, "prs_query_inst.cu"), os.path.join(obj_dir, "prs_query_%s_%d.o" % (t, k)),
-                      ["-DPRS_INST_T=%s" % t, "-DPRS_INST_K=%d" % k]))
+        inst = os.path.join(_SRC_DIR, "prs_query_inst.cu")
+        if k >= 16:  # wide top-k lists compile for minutes: one unit per target kind (lon/lat, separable, general)
+            for tk in (0, 1, 2):
+                units.append((inst, os.path.join(obj_dir, "prs_query_%s_%d_%d.o" % (t, k, tk)),
+                              ["-DPRS_INST_T=%s" % t, "-DPRS_INST_K=%d" % k, "-DPRS_INST_TK=%d" % tk]))
+        else:
+            units.append((inst, os.path.join(obj_dir, "prs_query_%s_%d.o" % (t, k)),
+                          ["-DPRS_INST_T=%s" % t, "-DPRS_INST_K=%d" % k]))
+    units.sort(key=lambda u: 0 if "_32_" in u[1] else 1 if "_16_" in u[1] else 2)  # longest first
 
     # kernel experiments: PRS_BUILD_ONLY="float_1,prs_b200" recompiles just those units and relinks with the
     # existing objects of the others (only sound while the structs shared between units are unchanged)

@@ -205,9 +205,11 @@ struct TargetTables {
 }  // namespace
 
 namespace prs {
-// defined in prs_query_inst.cu, one translation unit per (T, K)
-template <typename T, int K> int launch_query_tk(const QueryParams &P, const IndexView<T> &ix, int tk, cudaStream_t st);
-#define PRS_EXTERN_INST(T, K) extern template int launch_query_tk<T, K>(const QueryParams &, const IndexView<T> &, int, cudaStream_t);
+// launch_query_k<T, K, TK> is instantiated in the prs_query_inst.cu translation units, never here
+#define PRS_EXTERN_TK(T, K, TK) \
+    extern template int launch_query_k<T, K, TK>(const QueryParams &, const IndexView<T> &, cudaStream_t);
+#define PRS_EXTERN_INST(T, K) \
+    PRS_EXTERN_TK(T, K, PRS_TK_LONLAT) PRS_EXTERN_TK(T, K, PRS_TK_AREA_SEP) PRS_EXTERN_TK(T, K, PRS_TK_AREA_GEN)
 PRS_EXTERN_INST(float, 1)
 PRS_EXTERN_INST(float, 4)
 PRS_EXTERN_INST(float, 8)
@@ -218,6 +220,18 @@ PRS_EXTERN_INST(double, 4)
 PRS_EXTERN_INST(double, 8)
 PRS_EXTERN_INST(double, 16)
 PRS_EXTERN_INST(double, 32)
+
+template <typename T, int K> int launch_query_tk(const QueryParams &P, const IndexView<T> &ix, int tk, cudaStream_t st)
+{
+    switch (tk) {
+    case PRS_TK_LONLAT:
+        return launch_query_k<T, K, PRS_TK_LONLAT>(P, ix, st);
+    case PRS_TK_AREA_SEP:
+        return launch_query_k<T, K, PRS_TK_AREA_SEP>(P, ix, st);
+    default:
+        return launch_query_k<T, K, PRS_TK_AREA_GEN>(P, ix, st);
+    }
+}
 }  // namespace prs
 
 namespace {

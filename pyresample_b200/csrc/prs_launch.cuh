@@ -1,11 +1,12 @@
-// Host-side launch of the query kernel(s) for one (tree dtype, K) pair.  Each pair is instantiated in its own
-// translation unit (prs_query_inst.cu, compiled once per pair, in parallel) to keep the build time down.
+// Host-side launch of the query kernels for one (tree dtype, K, target kind).  launch_query_k is instantiated
+// explicitly in prs_query_inst.cu - one translation unit per (T, K), and per target kind for the wide top-k lists,
+// whose unrolled insertion networks take minutes to compile - so that the units build in parallel.
 #pragma once
 #include "prs_query.cuh"
 
 namespace prs {
 
-template <typename T, int K, int TK> inline int launch_query_k(const QueryParams &P, const IndexView<T> &ix, cudaStream_t st)
+template <typename T, int K, int TK> int launch_query_k(const QueryParams &P, const IndexView<T> &ix, cudaStream_t st)
 {
     if (P.n_t <= 0) return PRS_OK;
     int64_t tiles;
@@ -57,18 +58,6 @@ template <typename T> int launch_coverage_t(const QueryParams &P, int tk, uint8_
         return launch_coverage_k<T, PRS_TK_AREA_SEP>(P, cover, st);
     default:
         return launch_coverage_k<T, PRS_TK_AREA_GEN>(P, cover, st);
-    }
-}
-
-template <typename T, int K> int launch_query_tk(const QueryParams &P, const IndexView<T> &ix, int tk, cudaStream_t st)
-{
-    switch (tk) {
-    case PRS_TK_LONLAT:
-        return launch_query_k<T, K, PRS_TK_LONLAT>(P, ix, st);
-    case PRS_TK_AREA_SEP:
-        return launch_query_k<T, K, PRS_TK_AREA_SEP>(P, ix, st);
-    default:
-        return launch_query_k<T, K, PRS_TK_AREA_GEN>(P, ix, st);
     }
 }
 

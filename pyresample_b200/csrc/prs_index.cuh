@@ -428,7 +428,7 @@ __device__ __forceinline__ int64_t table_key(const FaceTable &t, int face, int i
 
 // Pass 2: exact ECEF coordinates of the kept points, their cell key and the histogram into table[key + 1].
 // tmp[i] = (x, y, z, cell key) - the record's source index is its position i, so the fourth word carries the key
-// to pass 3.  Points that are not kept are not written.
+// to pass 3.
 // SPARSE (a rank of a sharded run keeps a fraction of the points): the coordinates are only loaded for kept points;
 // otherwise all loads are issued up front.
 template <typename T, bool SPARSE>
@@ -456,7 +456,11 @@ __global__ void __launch_bounds__(BUILD_TPB)
 #pragma unroll
     for (int j = 0; j < BUILD_ITEMS; ++j) {
         const int64_t i = base + (int64_t)j * BUILD_TPB;
-        if (!kp[j]) continue;
+        if (!kp[j]) {
+            // dense builds mark the few skipped points in tmp, so that pass 3 needs nothing but tmp
+            if (!SPARSE && i < n) store_rec(tmp + i, (T)0, (T)0, (T)0, CELL_SKIP);
+            continue;
+        }
         T x, y, z;
         lonlat_to_xyz(lo[j], la[j], x, y, z);
         float fx, fy, fz;
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(BUILD_TPB)
 
 // Pass 3: scatter.  table[c + 1] holds start(c) after the exclusive scan and ends as start(c + 1).
 constexpr int SCATTER_ITEMS = 4;
-template <typename T>
+template <typename T, bool SPARSE>
 __global__ void __launch_bounds__(BUILD_TPB)
     build_scatter_kernel(const Rec<T> *__restrict__ tmp, const uint8_t *__restrict__ keep, int64_t n,
                          uint32_t *__restrict__ table, Rec<T> *__restrict__ recs)
@@ -482,15 +486,24 @@ __global__ void __launch_bounds__(BUILD_TPB)
     const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * SCATTER_ITEMS) + threadIdx.x;
     Rec<T> r[SCATTER_ITEMS];
     uint8_t kp[SCATTER_ITEMS];
+    // dense: every record was written by pass 2 (CELL_SKIP marks the skipped ones); sparse: only the records of
+    // kept points exist, the keep flags say which
 #pragma unroll
     for (int j = 0; j < SCATTER_ITEMS; ++j) {
         const int64_t i = base + (int64_t)j * BUILD_TPB;
-        kp[j] = i < n ? keep[i] : (uint8_t)0;
-    }
-#pragma unroll
-    for (int j = 0; j < SCATTER_ITEMS; ++j) {
         r[j].idx = CELL_SKIP;
-        if (kp[j]) r[j] = load_rec(tmp + base + (int64_t)j * BUILD_TPB);
+        kp[j] = 0;
+        if (i < n) {
+            if (SPARSE)
+                kp[j] = keep[i];
+            else
+                r[j] = load_rec(tmp + i);
+        }
+    }
+    if (SPARSE) {
+#pragma unroll
+        for (int j = 0; j < SCATTER_ITEMS; ++j)
+            if (kp[j]) r[j] = load_rec(tmp + base + (int64_t)j * BUILD_TPB);
     }
     // consecutive source points mostly share a cell: one atomic per (warp, cell) instead of one per point
     const unsigned lane = threadIdx.x & 31u;
@@ -684,8 +697,11 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
     PRS_CK(cudaMallocAsync((void **)&ix->recs, rec_bytes, st));
     timer.mark("records allocated");
     ix->bytes += rec_bytes;
-    build_scatter_kernel<T><<<(unsigned)((n + BUILD_TPB * SCATTER_ITEMS - 1) / (BUILD_TPB * SCATTER_ITEMS)), BUILD_TPB, 0, st>>>(
-        tmp, keep, n, ix->cell_start, (Rec<T> *)ix->recs);
+    const unsigned scatter_blocks = (unsigned)((n + BUILD_TPB * SCATTER_ITEMS - 1) / (BUILD_TPB * SCATTER_ITEMS));
+    if (ix->n_indexed * 2 < n)
+        build_scatter_kernel<T, true><<<scatter_blocks, BUILD_TPB, 0, st>>>(tmp, keep, n, ix->cell_start, (Rec<T> *)ix->recs);
+    else
+        build_scatter_kernel<T, false><<<scatter_blocks, BUILD_TPB, 0, st>>>(tmp, keep, n, ix->cell_start, (Rec<T> *)ix->recs);
     PRS_CKL();
     // coarse table
     PRS_CK(cudaMallocAsync((void **)&ix->coarse_alloc, sizeof(uint32_t) * (size_t)(nc + 4), st));

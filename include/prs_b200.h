@@ -174,6 +174,12 @@ int prs_index_info(const prs_index *index, int64_t info[8]);
 int prs_query(const prs_index *index, const prs_target *target, int k, double radius,
               uint32_t *idx_out, void *dist_out, uint8_t *valid_out, int64_t *flags_host, void *stream);
 
+/* The library keeps memory between calls: a grow-only workspace for the index build's temporaries (17 bytes per
+ * source point of the largest build so far, per device) and whatever the device's stream-ordered pool has cached.
+ * prs_release_cached_memory() waits for the current device, frees the workspace and trims the pool; live indexes
+ * are not touched.  Long-running services call it after an unusually large job. */
+int prs_release_cached_memory(void);
+
 /* ---- fused query + sample gather --------------------------------------------------------------------
  * resample_nearest (kd_tree.py:64-110) = get_neighbour_info + get_sample_from_neighbour_info('nn') without
  * materialising the neighbour arrays.  data: source rows of row_bytes bytes each, indexed by RAVELED SOURCE

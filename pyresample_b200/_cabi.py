@@ -29,7 +29,7 @@ PRS_TILE_ROWS = 8
 PRS_REDUCE_ALL, PRS_REDUCE_LAT_GE, PRS_REDUCE_LAT_LE, PRS_REDUCE_BOX, PRS_REDUCE_BOX_DATELINE = 0, 1, 2, 3, 4
 
 EXPORTED_SYMBOLS = (
-    "prs_abi_version", "prs_last_error", "prs_launch_count", "prs_lonlat_to_xyz", "prs_area_lonlats", "prs_valid_mask",
+    "prs_abi_version", "prs_last_error", "prs_launch_count", "prs_release_cached_memory", "prs_lonlat_to_xyz", "prs_area_lonlats", "prs_valid_mask",
     "prs_index_build", "prs_target_coverage", "prs_index_destroy", "prs_index_info", "prs_query", "prs_resample_nearest",
     "prs_resample_scratch_bytes", "prs_resample_nearest_fill", "prs_resample_nearest_search",
     "prs_resample_gauss", "prs_gather_nearest", "prs_gather_weighted", "prs_compact_rows",
@@ -146,6 +146,7 @@ def load_library():
         L.prs_last_error.argtypes = []
         L.prs_launch_count.restype = ctypes.c_int64
         L.prs_launch_count.argtypes = []
+        L.prs_release_cached_memory.argtypes = []
         L.prs_lonlat_to_xyz.argtypes = [vp, vp, i64, i32, vp, vp]
         L.prs_area_lonlats.argtypes = [ctypes.POINTER(prs_proj_params), ctypes.POINTER(prs_area_grid), i32,
                                        i64, i64, i64, i64, i64, i64, vp, vp, vp, vp]

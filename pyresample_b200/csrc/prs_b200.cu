@@ -351,6 +351,7 @@ int read_flags(unsigned int *flags_dev, int64_t *flags_host, cudaStream_t st)
 extern "C" {
 
 int prs_abi_version(void) { return PRS_ABI_VERSION; }
+int prs_release_cached_memory(void) { return prs::release_build_workspace(); }
 const char *prs_last_error(void) { return err_slot().c_str(); }
 int64_t prs_launch_count(void) { return (int64_t)launch_counter(); }
 

@@ -224,6 +224,23 @@ inline BuildWorkspace &build_workspace(int dev)
     static BuildWorkspace per_device[64];
     return per_device[dev < 0 || dev >= 64 ? 0 : dev];
 }
+inline int release_build_workspace()
+{
+    int dev = 0;
+    PRS_CK(cudaGetDevice(&dev));
+    BuildWorkspace &ws = build_workspace(dev);
+    std::lock_guard<std::mutex> guard(ws.lock);
+    PRS_CK(cudaDeviceSynchronize());
+    if (ws.buf) PRS_CK(cudaFree(ws.buf));
+    ws.buf = nullptr;
+    ws.capacity = 0;
+    ws.used = false;
+    cudaMemPool_t pool;
+    PRS_CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    PRS_CK(cudaMemPoolTrimTo(pool, 0));
+    return PRS_OK;
+}
+
 // RAII: acquire() takes the mutex and makes `st` wait for the previous user; the destructor records the event.
 struct WorkspaceLease {
     BuildWorkspace *ws = nullptr;

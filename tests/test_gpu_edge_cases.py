@@ -259,3 +259,61 @@ def test_device_neighbour_info_matches_get_sample(kd, geometry, tmp_path):
             assert np.array_equal(np.ma.getdata(got), np.ma.getdata(want))
     ref = kd_tree_ref.resample_nearest(swath, np.arange(30000.), area, 30000, fill_value=-1)
     assert np.array_equal(dev.sample_nearest(np.arange(30000.), area.shape, fill_value=-1), ref)
+
+
+def test_release_cached_memory_and_rebuild(kd, geometry, cuda_lib):
+    """prs_release_cached_memory frees the build workspace / pool cache; the next build simply allocates again."""
+    import torch
+    rng = np.random.default_rng(60)
+    lon, lat = rng.uniform(0, 10, 200000), rng.uniform(40, 50, 200000)
+    swath = geometry.SwathDefinition(lon, lat)
+    tgt = geometry.SwathDefinition(rng.uniform(0, 10, 1000), rng.uniform(40, 50, 1000))
+    a = kd.get_neighbour_info(swath, tgt, 20000, neighbours=1)
+    free0 = torch.cuda.mem_get_info()[0]
+    assert cuda_lib.prs_release_cached_memory() == 0
+    assert torch.cuda.mem_get_info()[0] >= free0
+    b = kd.get_neighbour_info(swath, tgt, 20000, neighbours=1)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomised_sweep_against_brute_force(kd, geometry, seed):
+    """Random source density, location, radius, k, dtype and target kind (swath or one of the area projections):
+    indices must equal the exhaustive checker's bit for bit (area targets: via the oracle's restated lon/lats)."""
+    from oracle import proj_ref
+    rng = np.random.default_rng(1000 + seed)
+    dtype = np.float32 if seed % 3 else np.float64
+    lon0, lat0 = rng.uniform(-180, 180), rng.uniform(-80, 80)
+    span = 10 ** rng.uniform(-0.5, 1.3)                 # 0.3 .. 20 degrees
+    n = int(10 ** rng.uniform(2.5, 4.3))
+    lon = ((lon0 + rng.uniform(-span, span, n) + 180) % 360) - 180
+    lat = np.clip(lat0 + rng.uniform(-span, span, n), -90, 90)
+    k = int(rng.choice([1, 1, 2, 4, 7, 8, 12, 16, 20, 32]))
+    spacing_m = 2 * span * 111e3 / np.sqrt(n)
+    radius = float(spacing_m * 10 ** rng.uniform(-0.3, 1.2))
+    kind = seed % 4
+    if kind == 0:
+        tlon = ((lon0 + rng.uniform(-1.3 * span, 1.3 * span, 1500) + 180) % 360) - 180
+        tlat = np.clip(lat0 + rng.uniform(-1.3 * span, 1.3 * span, 1500), -90, 90)
+    else:
+        half = 1.3 * span * 111e3
+        proj = {1: "+proj=laea +lat_0=%.3f +lon_0=%.3f +a=6371228.0 +units=m" % (lat0, lon0),
+                2: "+proj=stere +lat_0=%.3f +lon_0=%.3f +ellps=WGS84" % (lat0, lon0),
+                3: "+proj=eqc +lon_0=%.3f +datum=WGS84" % lon0}[kind]
+        y0 = 0.0 if kind != 3 else lat0 * 111e3
+        area = geometry.AreaDefinition("r", "r", "r", proj, 41, 37, (-half, y0 - half, half, y0 + half), dtype=dtype)
+        tlon, tlat = proj_ref.area_lonlats(area.proj_dict, area.area_extent, area.width, area.height, dtype=dtype)
+        tlon, tlat = tlon.ravel(), tlat.ravel()
+        ok = np.isfinite(tlon) & np.isfinite(tlat) & (np.abs(tlat) <= 90) & (np.abs(tlon) <= 180)
+        tlon, tlat = tlon[ok], tlat[ok]
+    _check_against_brute(kd, geometry, lon, lat, np.asarray(tlon, np.float64), np.asarray(tlat, np.float64), k,
+                         radius, dtype=dtype)
+    if kind != 0:
+        # the same target generated in-kernel from the AreaDefinition must agree with the explicit lon/lat target
+        swath = geometry.SwathDefinition(lon.astype(dtype), lat.astype(dtype))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a = kd.get_neighbour_info(swath, area, radius, neighbours=k, reduce_data=False)
+            want = kd_tree_ref.get_neighbour_info(swath, area, radius, neighbours=k, reduce_data=False)
+        assert np.array_equal(a[1], want[1]) and np.array_equal(a[2], want[2])

@@ -25,18 +25,25 @@ template <typename T, int K, int TK> int launch_query_k(const QueryParams &P, co
     if (P.stage == 0) PRS_CK(cudaMallocAsync((void **)&buf, sizeof(uint32_t) * (size_t)(tiles + 1), st));
     if (!buf) return fail(PRS_EINVAL, "staged call without scratch");
     uint32_t *n_live = buf, *live = buf + 1;
+    QueryParams Q = P;  // + the coordinate hand-over buffer where the target transform is expensive
+    void *xyz = nullptr;
+    if (TK != PRS_TK_AREA_SEP && P.stage == 0) {
+        PRS_CK(cudaMallocAsync(&xyz, 4 * sizeof(T) * (size_t)P.n_t, st));
+        Q.target_xyz = xyz;
+    }
     if (P.stage != 2) {
         PRS_CK(cudaMemsetAsync(n_live, 0, sizeof(uint32_t), st));
-        classify_kernel<T, K, TK><<<(unsigned)((tiles + QWARPS - 1) / QWARPS), QWARPS * 32, 0, st>>>(P, ix, (uint32_t)tiles, live, n_live);
+        classify_kernel<T, K, TK><<<(unsigned)((tiles + QWARPS - 1) / QWARPS), QWARPS * 32, 0, st>>>(Q, ix, (uint32_t)tiles, live, n_live);
         PRS_CKL();
     }
     if (P.stage != 1) {
         // search: persistent-style grid, a multiple of the SM count, blocks stride over the live list
         int64_t qgrid = (int64_t)n_sm * 32;
         if (qgrid > tiles) qgrid = tiles;
-        query_kernel<T, K, TK><<<(unsigned)qgrid, QROWS * 32, 0, st>>>(P, ix, live, n_live);
+        query_kernel<T, K, TK><<<(unsigned)qgrid, QROWS * 32, 0, st>>>(Q, ix, live, n_live);
         PRS_CKL();
     }
+    if (xyz) PRS_CK(cudaFreeAsync(xyz, st));
     if (P.stage == 0) PRS_CK(cudaFreeAsync(buf, st));
     return PRS_OK;
 }

@@ -441,6 +441,9 @@ struct QueryParams {
     void *stddev_out, *count_out;
     // staged execution (prs_resample_nearest_fill / _search): 0 = classify + fill + search in one call,
     // 1 = classify + fill only (live tiles listed in scratch), 2 = search the tiles listed in scratch
+    // targets whose coordinates are expensive (per-pixel inverse projection, explicit lon/lat): classification
+    // computes every point anyway and leaves (x, y, z, valid) here for the search (4 values of the tree dtype)
+    void *target_xyz;
     int stage;
     uint32_t *scratch;       // caller-owned: [0] = number of live tiles, [1..] = their ids
     uint8_t *tile_row_live;  // stage 1: [tile row] = 1 when the tile row holds a live tile
@@ -758,6 +761,30 @@ __device__ __forceinline__ float warp_min(float v)
     return v;
 }
 
+// Target coordinates handed from classification to the search: (x, y, z, valid != 0) per point.
+template <typename T> __device__ __forceinline__ void store_target_xyz(void *buf, int64_t p, T x, T y, T z, bool ok)
+{
+    if (sizeof(T) == 4) {
+        reinterpret_cast<float4 *>(buf)[p] = make_float4((float)x, (float)y, (float)z, ok ? 1.f : 0.f);
+    } else {
+        double2 *q = reinterpret_cast<double2 *>(buf) + 2 * p;
+        q[0] = make_double2((double)x, (double)y);
+        q[1] = make_double2((double)z, ok ? 1.0 : 0.0);
+    }
+}
+template <typename T> __device__ __forceinline__ bool load_target_xyz(const void *buf, int64_t p, T &x, T &y, T &z)
+{
+    if (sizeof(T) == 4) {
+        const float4 v = reinterpret_cast<const float4 *>(buf)[p];
+        x = (T)v.x, y = (T)v.y, z = (T)v.z;
+        return v.w != 0.f;
+    }
+    const double2 *q = reinterpret_cast<const double2 *>(buf) + 2 * p;
+    const double2 a = q[0], b = q[1];
+    x = (T)a.x, y = (T)a.y, z = (T)b.x;
+    return b.y != 0.0;
+}
+
 // Cap (unit centre c, squared chord d2m) around the valid points of a tile; false when the tile has none.
 // Separable projections: the tile is the product of <= 32 longitudes (one per lane) and QROWS latitudes, and
 //   u(j,l).c = sin(lat_j) sin(lat_c) + cos(lat_j) cos(lat_c) cos(lon_l - lon_c)
@@ -811,7 +838,9 @@ __device__ __forceinline__ bool tile_cap(const QueryParams &P, uint32_t tile, in
         ux[j] = uy[j] = uz[j] = 0.f;
         if (p >= 0) {
             T qx, qy, qz;
-            if (target_point<T, TK>(P, p, trow0 + j, tcol, qx, qy, qz)) {
+            const bool ok = target_point<T, TK>(P, p, trow0 + j, tcol, qx, qy, qz);
+            if (P.target_xyz) store_target_xyz<T>(P.target_xyz, p, qx, qy, qz, ok);
+            if (ok) {
                 vmask |= 1u << j;
                 ux[j] = (float)qx * invR;
                 uy[j] = (float)qy * invR;
@@ -942,7 +971,12 @@ __device__ __forceinline__ void query_tile(const QueryParams &P, const IndexView
     trow += warp;
     T qx = 0, qy = 0, qz = 0;
     bool valid = false;
-    if (p >= 0) valid = target_point<T, TK>(P, p, trow, tcol, qx, qy, qz);
+    if (p >= 0) {
+        if (TK != PRS_TK_AREA_SEP && P.target_xyz)
+            valid = load_target_xyz<T>(P.target_xyz, p, qx, qy, qz);  // classification has been here
+        else
+            valid = target_point<T, TK>(P, p, trow, tcol, qx, qy, qz);
+    }
     TopK<T, K> top;
     top.init();
     if (valid) knn_search<T, K>(ix, qx, qy, qz, dub, s2r, sr, top);

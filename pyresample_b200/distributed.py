@@ -145,6 +145,7 @@ class _UploadAndBroadcast(object):
     def __init__(self, host_rows, shape, src, group):
         self.host_rows, self.shape, self.src, self.group = host_rows, tuple(shape), src, group
         self.row_bytes = self.shape[1]
+        self.start_early = True
 
     def start(self, main, up):
         import torch
@@ -153,7 +154,8 @@ class _UploadAndBroadcast(object):
         if rank == self.src:
             up.wait_stream(main)
             with torch.cuda.stream(up):
-                self.dev = torch.from_numpy(self.host_rows).cuda(non_blocking=True)
+                from . import kd_tree
+                self.dev = kd_tree._dev(self.host_rows)
                 self.ready = torch.cuda.Event()
                 self.ready.record(up)
         else:

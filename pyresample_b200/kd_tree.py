@@ -17,6 +17,7 @@ fused entry points.  There is no CPU fallback: without the CUDA library and a GP
 from __future__ import annotations
 
 import ctypes
+import threading
 import time
 import types
 import warnings
@@ -67,6 +68,58 @@ def _np_dtype_of(x):
     return np.dtype(x.dtype)
 
 
+# Ordinary (pageable) numpy arrays of at least _STAGED_MIN_BYTES go up in chunks through a few pinned staging
+# buffers that a small thread pool fills (numpy releases the GIL while copying) while earlier chunks are already on
+# the bus: ~3x the rate of a plain pageable cudaMemcpy, which is bound by one thread's memcpy.
+_STAGED_MIN_BYTES = 16 << 20
+_STAGE_CHUNK = 8 << 20
+_STAGE_BUFFERS = 6
+_STAGE_THREADS = 4
+_stage = {"lock": threading.Lock(), "bufs": None, "pool": None}
+
+
+def _staged_upload(a):
+    """Contiguous pageable numpy array -> CUDA tensor of the same dtype / shape on the current stream."""
+    torch = _torch()
+    flat = a.reshape(-1).view(np.uint8)
+    n = flat.size
+    dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    with _stage["lock"]:
+        if _stage["bufs"] is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _stage["bufs"] = [[torch.empty(_STAGE_CHUNK, dtype=torch.uint8, pin_memory=True), None]
+                              for _ in range(_STAGE_BUFFERS)]
+            for b in _stage["bufs"]:
+                b.append(b[0].numpy())
+            _stage["pool"] = ThreadPoolExecutor(max_workers=_STAGE_THREADS)
+        bufs, pool = _stage["bufs"], _stage["pool"]
+        n_chunks = (n + _STAGE_CHUNK - 1) // _STAGE_CHUNK
+
+        def fill(i):
+            b = bufs[i % _STAGE_BUFFERS]
+            if b[1] is not None:
+                b[1].synchronize()  # the previous transfer out of this buffer has finished
+            off = i * _STAGE_CHUNK
+            m = min(_STAGE_CHUNK, n - off)
+            return pool.submit(np.copyto, b[2][:m], flat[off:off + m])
+
+        pending = [(i, fill(i)) for i in range(min(_STAGE_BUFFERS, n_chunks))]
+        while pending:
+            i, fut = pending.pop(0)
+            fut.result()
+            b = bufs[i % _STAGE_BUFFERS]
+            off = i * _STAGE_CHUNK
+            m = min(_STAGE_CHUNK, n - off)
+            dev[off:off + m].copy_(b[0][:m], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            b[1] = ev
+            if i + _STAGE_BUFFERS < n_chunks:
+                pending.append((i + _STAGE_BUFFERS, fill(i + _STAGE_BUFFERS)))
+    return dev.view(getattr(torch, a.dtype.name)).reshape(a.shape)
+
+
 def _dev(x, dtype=None):
     """numpy array / torch tensor -> contiguous CUDA tensor (optionally cast)."""
     torch = _torch()
@@ -78,7 +131,11 @@ def _dev(x, dtype=None):
             a = a.view(np.uint8)
         if not a.flags.writeable:
             a = a.copy()
-        t = torch.from_numpy(a).cuda(non_blocking=True)
+        h = torch.from_numpy(a)
+        if a.nbytes >= _STAGED_MIN_BYTES and not h.is_pinned():
+            t = _staged_upload(a)
+        else:
+            t = h.cuda(non_blocking=True)
     if dtype is not None:
         td = getattr(torch, np.dtype(dtype).name)
         if t.dtype != td:
@@ -133,6 +190,9 @@ class _HostUpload(object):
     def __init__(self, host_rows):
         self.host_rows = host_rows
         self.row_bytes = host_rows.shape[1]
+        # pinned memory goes up asynchronously: start right away.  Pageable memory keeps this thread busy while it
+        # is staged (_staged_upload): start once the early read-back has been queued.
+        self.start_early = bool(_torch().from_numpy(np.ascontiguousarray(host_rows)).is_pinned())
 
     def start(self, main, up):
         torch = _torch()
@@ -163,7 +223,9 @@ def _nearest_pipelined(L, source, tg, n_t, arrival, fill_row_host, radius):
     row_bytes = arrival.row_bytes
     width, nrows = int(tg.grid.width), int(tg.nrows)
     stamps = [("enter", time.perf_counter())] if _TIMELINE is not None else None
-    arrival.start(main, up)
+    early = getattr(arrival, "start_early", True)
+    if early:
+        arrival.start(main, up)
     fill_row = _dev(fill_row_host)
     out = torch.empty((n_t, row_bytes), dtype=torch.uint8, device="cuda")
     scratch = torch.empty(int(L.prs_resample_scratch_bytes(ctypes.byref(tg))), dtype=torch.uint8, device="cuda")
@@ -181,6 +243,8 @@ def _nearest_pipelined(L, source, tg, n_t, arrival, fill_row_host, radius):
         for r0, r1, is_live in runs:
             if not is_live:
                 host_out[r0 * width:r1 * width].copy_(out[r0 * width:r1 * width], non_blocking=True)
+    if not early:
+        arrival.start(main, up)
     dev_data = arrival.finish(main)
     _cabi.check(L.prs_resample_nearest_search(handle, ctypes.byref(tg), float(radius), _ptr(dev_data), row_bytes,
                                               _ptr(fill_row), _ptr(out), _ptr(scratch), _stream()))

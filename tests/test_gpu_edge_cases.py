@@ -317,3 +317,22 @@ def test_randomised_sweep_against_brute_force(kd, geometry, seed):
             a = kd.get_neighbour_info(swath, area, radius, neighbours=k, reduce_data=False)
             want = kd_tree_ref.get_neighbour_info(swath, area, radius, neighbours=k, reduce_data=False)
         assert np.array_equal(a[1], want[1]) and np.array_equal(a[2], want[2])
+
+
+def test_staged_upload_of_pageable_arrays(kd, monkeypatch):
+    """Large ordinary numpy arrays go up through pinned staging buffers in chunks; the tensor must equal the array
+    for every size around the chunk / buffer-count boundaries and for every dtype width."""
+    monkeypatch.setattr(kd, "_STAGED_MIN_BYTES", 1)
+    monkeypatch.setattr(kd, "_STAGE_CHUNK", 1 << 16)
+    monkeypatch.setitem(kd._stage, "bufs", None)
+    rng = np.random.default_rng(61)
+    chunk = 1 << 16
+    for nbytes in (1, chunk - 1, chunk, chunk + 1, 6 * chunk, 6 * chunk + 5, 13 * chunk + 12345):
+        a = rng.integers(0, 255, nbytes, dtype=np.uint8)
+        assert np.array_equal(kd._dev(a).cpu().numpy(), a)
+    for dt in (np.float32, np.float64, np.int16, np.bool_):
+        a = (rng.random((1237, 219)) * 100).astype(dt)
+        t = kd._dev(a)
+        assert tuple(t.shape) == a.shape
+        assert np.array_equal(t.cpu().numpy().astype(dt), a)
+    monkeypatch.setitem(kd._stage, "bufs", None)  # full-size buffers again for whoever comes next

@@ -972,6 +972,17 @@ def _scatter_full(rows_t, voi_t, output_size, fill_row_t):
     return out
 
 
+def _weights_finite_at_one(weight_funcs):
+    """True when every weight function maps the distance 1 (what missing neighbours are given, kd_tree.py:767-768)
+    to a finite value, so that ``0 * w`` is 0 for them."""
+    funcs = weight_funcs if isinstance(weight_funcs, (list, tuple)) else [weight_funcs]
+    try:
+        with np.errstate(all="ignore"):
+            return all(bool(np.all(np.isfinite(np.asarray(f(np.ones(1)), dtype=np.float64)))) for f in funcs)
+    except Exception:  # a function that does not take a length-1 array: no shortcut
+        return False
+
+
 def _eval_weight_planes(weight_funcs, channels, is_multi, dist_np, index_missing):
     """Evaluate arbitrary Python weight functions on the host distances (kd_tree.py:764-787).
 
@@ -1152,6 +1163,15 @@ def _resample(source_geo_def, data, target_geo_def, resample_type,
             idx, dist, valid, kth_found, n_invalid = _query_device(source, tgt, radius_of_influence, neighbours,
                                                                    reduce_data)
             voi_t = None
+            if _weights_finite_at_one(weight_funcs):
+                # pixels without any neighbour end as fill / NaN / 0 whatever the weights are (norm == 0,
+                # kd_tree.py:807-809, 842-858) as long as f(1) - the value the reference feeds for missing
+                # neighbours - is finite: only rows with a neighbour travel to the host and back
+                has = (idx[:, 0] >= 0) & (idx[:, 0] < int(source.n_valid))
+                n_has = int(has.sum())
+                if 0 < n_has < idx.shape[0] // 2:
+                    valid = has.to(torch.uint8)
+                    n_invalid = idx.shape[0] - n_has
             if n_invalid:
                 voi_t = valid
                 idx = _compact_rows(valid, idx)

@@ -336,3 +336,41 @@ def test_staged_upload_of_pageable_arrays(kd, monkeypatch):
         assert tuple(t.shape) == a.shape
         assert np.array_equal(t.cpu().numpy().astype(dt), a)
     monkeypatch.setitem(kd._stage, "bufs", None)  # full-size buffers again for whoever comes next
+
+
+def test_custom_weights_on_sparse_coverage(kd, geometry):
+    """Python weight functions on a grid that is mostly outside the swath: only rows with a neighbour are evaluated
+    on the host, the rest must still come out as fill / NaN / 0 like in the reference."""
+    rng = np.random.default_rng(62)
+    lon, lat = rng.uniform(8, 12, 20000), rng.uniform(48, 52, 20000)
+    swath = geometry.SwathDefinition(lon, lat)
+    area = geometry.AreaDefinition("w", "w", "w", "+proj=eqc +datum=WGS84", 300, 200,
+                                   (-3000000.0, 2000000.0, 5000000.0, 8000000.0))
+    data = rng.normal(size=20000)
+    data2 = np.column_stack([data, data * 2 + 1])
+
+    def wf(d):
+        return 1 - d / 60000.0
+
+    def wf2(d):
+        return np.exp(-d ** 2 / 30000.0 ** 2)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = kd.resample_custom(swath, data, area, 60000, wf, neighbours=6, fill_value=-7)
+        want = kd_tree_ref.resample_custom(swath, data, area, 60000, wf, neighbours=6, fill_value=-7)
+        assert (want == -7).mean() > 0.8
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9)
+        got = kd.resample_custom(swath, data2, area, 60000, [wf, wf2], neighbours=6, fill_value=None, with_uncert=True)
+        want = kd_tree_ref.resample_custom(swath, data2, area, 60000, [wf, wf2], neighbours=6, fill_value=None,
+                                           with_uncert=True)
+        for g, w in zip(got, want):
+            assert np.array_equal(np.ma.getmaskarray(g), np.ma.getmaskarray(w))
+            np.testing.assert_allclose(np.ma.getdata(g)[~np.ma.getmaskarray(g)],
+                                       np.ma.getdata(w)[~np.ma.getmaskarray(w)], rtol=1e-6, atol=1e-9)
+        # a weight function that is not finite at 1: no shortcut, same answer as the reference
+        def bad(d):
+            return 1.0 / (d - 1.0)
+        got = kd.resample_custom(swath, data, area, 60000, bad, neighbours=3, fill_value=-7)
+        want = kd_tree_ref.resample_custom(swath, data, area, 60000, bad, neighbours=3, fill_value=-7)
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9, equal_nan=True)

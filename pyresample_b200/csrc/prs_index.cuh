@@ -293,6 +293,9 @@ struct BuildTimer {
     }
 };
 
+#ifndef PRS_SELECT_MIN_BLOCKS
+#define PRS_SELECT_MIN_BLOCKS 8  // 32 registers, no spills: full occupancy for the issue-bound selection pass
+#endif
 constexpr int BUILD_TPB = 256;
 constexpr int BUILD_ITEMS = 4;  // points per thread in the build passes
 
@@ -305,7 +308,7 @@ constexpr int BUILD_ITEMS = 4;  // points per thread in the build passes
 // kilometres wide and both masks carry a whole cell of slack.  The exact ECEF transform runs in pass 2, for the
 // points that are kept, once the cell size is known.
 template <typename T>
-__global__ void __launch_bounds__(BUILD_TPB)
+__global__ void __launch_bounds__(BUILD_TPB, PRS_SELECT_MIN_BLOCKS)
     build_select_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, uint8_t *__restrict__ valid,
                         int compute_valid, const BoxT<T> box, const uint8_t *__restrict__ premask,
                         const uint8_t *__restrict__ exclude, const uint8_t *__restrict__ cover,

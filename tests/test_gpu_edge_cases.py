@@ -374,3 +374,52 @@ def test_custom_weights_on_sparse_coverage(kd, geometry):
         got = kd.resample_custom(swath, data, area, 60000, bad, neighbours=3, fill_value=-7)
         want = kd_tree_ref.resample_custom(swath, data, area, 60000, bad, neighbours=3, fill_value=-7)
         np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9, equal_nan=True)
+
+
+def test_concurrent_calls_from_threads(kd, geometry, monkeypatch):
+    """SURVEY 8b threading: calls from several Python threads (each on its own CUDA stream) must not disturb each
+    other - the build workspace, the staging buffers and the side streams are shared process-wide."""
+    import threading
+
+    import torch
+    monkeypatch.setattr(kd, "_PIPELINE_MIN_BYTES", 0)      # take the pipelined path
+    monkeypatch.setattr(kd, "_STAGED_MIN_BYTES", 1 << 16)  # and the staged upload
+    area = geometry.AreaDefinition("t", "t", "t", "+proj=eqc +datum=WGS84", 700, 400,
+                                   (-2000000.0, 3000000.0, 4000000.0, 7500000.0))
+    jobs = []
+    for s in range(4):
+        rng = np.random.default_rng(70 + s)
+        lon, lat = rng.uniform(-10 + 5 * s, 20 + 5 * s, 60000), rng.uniform(30, 60, 60000)
+        data = rng.normal(size=(60000, 2)).astype(np.float32)
+        jobs.append((geometry.SwathDefinition(lon.astype(np.float32), lat.astype(np.float32)), data))
+
+    def work(job):
+        swath, data = job
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a = kd.resample_nearest(swath, data, area, 25000, fill_value=-1)
+            b = kd.get_neighbour_info(swath, area, 25000, neighbours=4)
+        return a, b
+
+    expected = [work(j) for j in jobs]
+    results = [None] * len(jobs)
+    errors = []
+
+    def runner(i):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(3):
+                    results[i] = work(jobs[i])
+        except Exception as exc:  # pragma: no cover - reported below
+            errors.append(exc)
+
+    threads = [threading.Thread(target=runner, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for (a, b), (ea, eb) in zip(results, expected):
+        assert np.array_equal(a, ea)
+        for x, y in zip(b, eb):
+            assert np.array_equal(x, y)

@@ -353,6 +353,13 @@ __device__ __forceinline__ void knn_search(const IndexView<T> &ix, T qx, T qy, T
             s2 = __ldg(row + 2 * fw + hb.u0);
             e2 = __ldg(row + 2 * fw + hb.u1 + 1);
         }
+        // walk the point's own row of cells first: its candidates are the likeliest neighbours, so the k-th
+        // distance tightens early and fewer of the later candidates have to be inserted into the list
+        if (K > 1 && nrows > 1 && cv != hb.v0) {
+            const uint32_t ts = s0, te = e0;
+            s0 = s1, e0 = e1;
+            s1 = ts, e1 = te;
+        }
         const uint32_t n0 = e0 - s0, n01 = n0 + (e1 - s1), total = n01 + (e2 - s2);
         // records are fetched PRS_SCAN_BATCH at a time before any is examined: the loads of a batch are in flight
         // together (one load per iteration left the thread waiting a full memory round trip per candidate)

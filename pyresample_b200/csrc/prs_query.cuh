@@ -46,10 +46,21 @@ template <typename T, int K> struct TopK {
             id[i] = PRS_NONE;
         }
     }
+    // (a, ia) before (b, ib) in the list order.  float: squared distances are >= +0 and never NaN, so their bit
+    // patterns order like unsigned integers and (bits << 32 | index) compares both fields at once.
+    static __device__ __forceinline__ bool before(T a, uint32_t ia, T b, uint32_t ib)
+    {
+        if (sizeof(T) == 4) {
+            const unsigned long long ka = ((unsigned long long)__float_as_uint((float)a) << 32) | ia;
+            const unsigned long long kb = ((unsigned long long)__float_as_uint((float)b) << 32) | ib;
+            return ka < kb;
+        }
+        return a < b || (a == b && ia < ib);
+    }
     __device__ __forceinline__ void offer(T d2, uint32_t idx, T dub)
     {
         if (!(d2 < dub)) return;  // strict radius test in the tree dtype (pykdtree)
-        if (d2 < d[K - 1] || (d2 == d[K - 1] && idx < id[K - 1])) {
+        if (before(d2, idx, d[K - 1], id[K - 1])) {
             if (K > 1) {  // a cell may be visited twice (overlapping phases): never list a point twice
                 bool dup = false;
 #pragma unroll
@@ -60,7 +71,7 @@ template <typename T, int K> struct TopK {
             id[K - 1] = idx;
 #pragma unroll
             for (int j = K - 1; j > 0; --j) {
-                bool sw = d[j] < d[j - 1] || (d[j] == d[j - 1] && id[j] < id[j - 1]);
+                bool sw = before(d[j], id[j], d[j - 1], id[j - 1]);
                 T td = d[j - 1];
                 uint32_t ti = id[j - 1];
                 d[j - 1] = sw ? d[j] : td;

@@ -33,6 +33,10 @@ constexpr int STAGE_ROW_BYTES = 64; // nearest rows up to this size are staged t
 #define PRS_SCAN_BATCH(K) ((K) <= 4 ? 4 : 2)
 #endif
 
+#ifndef PRS_TOPK_BUBBLE
+#define PRS_TOPK_BUBBLE 0
+#endif
+
 // ------------------------------------------------------------------------------------------ top-k list
 // Sorted ascending by (d2, source index): ties go to the lowest source index (BASELINE north_star).
 template <typename T, int K> struct TopK {
@@ -67,6 +71,7 @@ template <typename T, int K> struct TopK {
                 for (int j = 0; j < K - 1; ++j) dup = dup || (id[j] == idx);
                 if (dup) return;
             }
+#if PRS_TOPK_BUBBLE
             d[K - 1] = d2;
             id[K - 1] = idx;
 #pragma unroll
@@ -79,6 +84,22 @@ template <typename T, int K> struct TopK {
                 d[j] = sw ? td : d[j];
                 id[j] = sw ? ti : id[j];
             }
+#else
+            // every slot decides for itself (no chain of dependent swaps): slot j takes its upper neighbour when
+            // the candidate goes above that neighbour, the candidate when it goes exactly here, else keeps its entry
+            bool lt[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) lt[j] = before(d2, idx, d[j], id[j]);
+#pragma unroll
+            for (int j = K - 1; j > 0; --j) {
+                const T nd = lt[j] ? d2 : d[j];
+                const uint32_t ni = lt[j] ? idx : id[j];
+                d[j] = lt[j - 1] ? d[j - 1] : nd;
+                id[j] = lt[j - 1] ? id[j - 1] : ni;
+            }
+            d[0] = lt[0] ? d2 : d[0];
+            id[0] = lt[0] ? idx : id[0];
+#endif
         }
     }
     __device__ __forceinline__ bool full() const { return id[K - 1] != PRS_NONE; }

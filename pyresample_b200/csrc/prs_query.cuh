@@ -61,11 +61,12 @@ template <typename T, int K> struct TopK {
         }
         return a < b || (a == b && ia < ib);
     }
-    __device__ __forceinline__ void offer(T d2, uint32_t idx, T dub)
+    // CHECK_DUP = false where every record is seen at most once (the first walk over the 3x3 block)
+    template <bool CHECK_DUP = true> __device__ __forceinline__ void offer(T d2, uint32_t idx, T dub)
     {
         if (!(d2 < dub)) return;  // strict radius test in the tree dtype (pykdtree)
         if (before(d2, idx, d[K - 1], id[K - 1])) {
-            if (K > 1) {  // a cell may be visited twice (overlapping phases): never list a point twice
+            if (K > 1 && CHECK_DUP) {  // a cell may be visited twice (overlapping phases): never list a point twice
                 bool dup = false;
 #pragma unroll
                 for (int j = 0; j < K - 1; ++j) dup = dup || (id[j] == idx);
@@ -407,7 +408,8 @@ __device__ __forceinline__ void knn_search(const IndexView<T> &ix, T qx, T qy, T
             }
 #pragma unroll
             for (int u = 0; u < B; ++u)
-                if (t0 + u < total) top.offer(dist2<T>(qx, qy, qz, r[u].x, r[u].y, r[u].z), r[u].idx, dub);
+                if (t0 + u < total)
+                    top.template offer<false>(dist2<T>(qx, qy, qz, r[u].x, r[u].y, r[u].z), r[u].idx, dub);
         }
     } else {
         hb.u0 = hb.v0 = 1;  // home block outside the table: nothing visited

@@ -188,3 +188,29 @@ def test_neighbour_info_file_round_trip(tmp_path):
     nc.save_neighbour_info(path, np.zeros(5, bool), np.ones(6, bool), np.full(6, 5, np.int32), None)
     v1, v2, i2, d2 = nc.load_neighbour_info(path)
     assert not v1.any() and v2.all() and i2.dtype == np.int32 and d2 is None
+
+
+def test_registry_and_small_helpers_without_gpu():
+    """The resampler registry, the weight-function probe and the index downcast are pure host logic."""
+    from pyresample_b200 import future_nearest, kd_tree, registry, utils
+    assert registry.list_resamplers() == ["nearest"]
+    assert registry.RESAMPLER_REGISTRY["nearest"] is future_nearest.KDTreeNearestXarrayResampler
+    with pytest.raises(ValueError, match="already registered"):
+        registry.register_resampler("nearest", object)
+    assert kd_tree._weights_finite_at_one(lambda d: 1 - d / 1000.0)
+    assert kd_tree._weights_finite_at_one([lambda d: np.exp(-d), lambda d: d * 0 + 2])
+    assert not kd_tree._weights_finite_at_one(lambda d: 1.0 / (d - 1.0))
+    assert not kd_tree._weights_finite_at_one(lambda d: d["no such key"])
+    idx = np.array([[0, 5, -1], [7, 9, 3]], dtype=np.int32)
+    down = utils._downcast_index_array(idx.copy(), 8)
+    assert down.dtype == np.uint16 and np.array_equal(down, [[0, 5, 8], [7, 8, 3]])
+    big = utils._downcast_index_array(idx.copy(), 70000)
+    assert big.dtype == np.int32 and np.array_equal(big, idx)
+    assert utils.fwhm2sigma(2 * np.sqrt(np.log(2))) == pytest.approx(1.0)
+    area = geometry.AreaDefinition("a", "a", "a", "+proj=eqc +datum=WGS84", 10, 10, (0, 0, 1e6, 1e6))
+    with pytest.raises(ValueError, match="2 dimensions"):
+        future_nearest.KDTreeNearestXarrayResampler(area, geometry.SwathDefinition(np.zeros(3), np.zeros(3)))
+    r = registry.create_resampler(area, area)
+    assert r.version == "0.1" and r._get_src_geo_dims() == ('y', 'x')
+    with pytest.raises(ValueError, match="not the same shape"):
+        r.precompute(mask=np.zeros((3, 3), dtype=bool))

@@ -423,3 +423,30 @@ def test_concurrent_calls_from_threads(kd, geometry, monkeypatch):
         assert np.array_equal(a, ea)
         for x, y in zip(b, eb):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("dtype,channels", [(np.uint8, 1), (np.int16, 3), (np.float64, 7), (np.float64, 9),
+                                            (np.complex64, 1)])
+def test_pipelined_nearest_row_layouts(kd, geometry, monkeypatch, dtype, channels):
+    """Row sizes that take the other store paths of the fill / search stages (1, 6, 56, 72 and 8 bytes per pixel)."""
+    rng = np.random.default_rng(63)
+    lon = rng.uniform(-15, 35, 80000).astype(np.float32)
+    lat = rng.uniform(20, 45, 80000).astype(np.float32)
+    shape = (80000,) if channels == 1 else (80000, channels)
+    if np.issubdtype(dtype, np.complexfloating):
+        data = (rng.normal(size=shape) + 1j * rng.normal(size=shape)).astype(dtype)
+    elif np.issubdtype(dtype, np.integer):
+        data = rng.integers(0, 100, size=shape).astype(dtype)
+    else:
+        data = rng.normal(size=shape).astype(dtype)
+    swath = geometry.SwathDefinition(lon, lat)
+    area = geometry.AreaDefinition("g", "g", "g", "+proj=eqc +datum=WGS84", 1003, 517,
+                                   (-10018754.17, -8000000.0, 10018754.17, 9000000.0))
+    plain = kd.resample_nearest(swath, data, area, 30000, fill_value=7)
+    monkeypatch.setattr(kd, "_PIPELINE_MIN_BYTES", 0)
+    monkeypatch.setattr(kd, "_PIPELINE_MIN_RUN_BYTES", 0)
+    piped = kd.resample_nearest(swath, data, area, 30000, fill_value=7)
+    assert piped.dtype == plain.dtype == data.dtype and piped.shape == plain.shape
+    assert np.array_equal(piped, plain)
+    want = kd_tree_ref.resample_nearest(swath, data, area, 30000, fill_value=7)
+    assert np.array_equal(piped, want)

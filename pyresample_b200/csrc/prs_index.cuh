@@ -419,14 +419,32 @@ static __global__ void build_reduce_kernel(const uint8_t *__restrict__ occ, cons
         nv += c.x;
         ns += c.y;
     }
-    for (int i = tid; i < 6 * OCC_G * OCC_G; i += nth) {
-        if (!occ[i]) continue;
-        int f = i / (OCC_G * OCC_G), iv = (i / OCC_G) % OCC_G, iu = i % OCC_G;
-        atomicMin(&rect[4 * f + 0], iu);
-        atomicMin(&rect[4 * f + 1], iv);
-        atomicMax(&rect[4 * f + 2], iu);
-        atomicMax(&rect[4 * f + 3], iv);
-        ++no;
+    // four probe cells per thread (one 32-bit load); a warp covers one row of OCC_G = 128 cells of one face, so
+    // its bounding box is reduced in registers and costs at most four atomics
+    static_assert(OCC_G == 128, "a warp reads exactly one row of probe cells");
+    const uint32_t *occ4 = reinterpret_cast<const uint32_t *>(occ);
+    for (int w = tid; w < 6 * OCC_G * OCC_G / 4; w += nth) {
+        const uint32_t bits = occ4[w];
+        const int i = w * 4, f = i / (OCC_G * OCC_G), iv = (i / OCC_G) % OCC_G, iu = i % OCC_G;
+        int u0 = 1 << 30, u1 = -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((bits >> (8 * k)) & 0xFFu) {
+                u0 = min(u0, iu + k);
+                u1 = max(u1, iu + k);
+                ++no;
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            u0 = min(u0, __shfl_xor_sync(0xffffffffu, u0, o));
+            u1 = max(u1, __shfl_xor_sync(0xffffffffu, u1, o));
+        }
+        if ((threadIdx.x & 31) == 0 && u1 >= 0) {
+            atomicMin(&rect[4 * f + 0], u0);
+            atomicMin(&rect[4 * f + 1], iv);
+            atomicMax(&rect[4 * f + 2], u1);
+            atomicMax(&rect[4 * f + 3], iv);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -257,7 +257,7 @@ class XArrayResamplerNN(object):
         src_geo_dims, dst_geo_dims = self._get_valid_dims(data)
 
         def contain_coords(var, coord_list):
-            return bool(set(coord_list).intersection(set(var.dims)))
+            return bool(set(coord_list).intersection(set(getattr(var, "dims", ()))))
 
         coords = {c: c_var for c, c_var in data.coords.items()
                   if not contain_coords(c_var, src_geo_dims + dst_geo_dims)}

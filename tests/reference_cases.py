@@ -379,3 +379,22 @@ def image_fixtures(geometry):
 
 IMAGE_NEAREST_SUM = 399936.70287099993        # test_image.py:130-138
 IMAGE_NEAREST_RESIZE_SUM = 2212023.0175830    # test_image.py:140-148
+
+
+# --------------------------------------------------------------- XArrayResamplerNN literals (test_kd_tree.py:743-995)
+def xarray_nn_fixtures(geometry):
+    """The class fixtures of TestXArrayResamplerNN: note src_area_2d is 50 wide x 10 high while the data are (50, 10) -
+    the reference only ravels, so the sizes match (500) and the literals below depend on exactly that."""
+    stere = {'a': '6378144.0', 'b': '6356759.0', 'proj': 'stere'}
+    extent = [-1370912.72, -909968.64000000001, 1029087.28, 1490031.3600000001]
+    area_def = geometry.AreaDefinition('areaD', 'Europe (3km, HRV, VTC)', 'areaD',
+                                       dict(stere, lat_0='50.00', lat_ts='50.00', lon_0='8.00'), 800, 800, extent)
+    src_area_2d = geometry.AreaDefinition('areaD_src', 'Europe (3km, HRV, VTC)', 'areaD',
+                                          dict(stere, lat_0='52.00', lat_ts='52.00', lon_0='5.00'), 50, 10, extent)
+    data_2d = np.fromfunction(lambda y, x: y * x, (50, 10))
+    data_3d = np.fromfunction(lambda y, x, b: y * x * b, (50, 10, 3))
+    return area_def, src_area_2d, data_2d, data_3d
+
+
+XARRAY_NN_SUMS = {"area_to_area": 27706753.0, "area_no_roi": 87281406.0, "area_no_roi_no_geocentric": 1855928.0,
+                  "area_3d": 83120259.0}

@@ -161,3 +161,37 @@ def test_xarray_resampler_nn_swath_to_area(kd):
     # default radius from the geometries' geocentric resolution (kd_tree.py:949-968)
     auto = kd.XArrayResamplerNN(swath_np, area)
     assert 1000 < auto.radius_of_influence < 200000
+
+
+def test_xarray_resampler_nn_reference_literals(kd, monkeypatch):
+    """test_kd_tree.py:897-995 replayed on the GPU class: area -> area, with / without radius, 3-D data, and the
+    dimension-name check that precedes them."""
+    import reference_cases as rc
+    from pyresample_b200 import geometry
+    area_def, src, d2, d3 = rc.xarray_nn_fixtures(geometry)
+    S = rc.XARRAY_NN_SUMS
+    resampler = kd.XArrayResamplerNN(src, area_def, radius_of_influence=50000, neighbours=1)
+    ninfo = resampler.get_neighbour_info()
+    assert _values(ninfo[2]).shape == (800, 800, 1)
+    with pytest.raises(ValueError):
+        resampler.get_sample_from_neighbour_info(FakeDataArray(d2, dims=('my_dim_y', 'my_dim_x')))
+    res = resampler.get_sample_from_neighbour_info(FakeDataArray(d2, dims=('y', 'x')))
+    assert np.nansum(_values(res)) == S["area_to_area"]
+    res3 = resampler.get_sample_from_neighbour_info(
+        FakeDataArray(d3, dims=('y', 'x', 'bands'), coords={'bands': ['r', 'g', 'b']}))
+    assert sorted(res3.coords['bands']) == ['b', 'g', 'r'] and np.nansum(_values(res3)) == S["area_3d"]
+    auto = kd.XArrayResamplerNN(src, area_def, neighbours=1)
+    auto.get_neighbour_info()
+    assert np.nansum(_values(auto.get_sample_from_neighbour_info(FakeDataArray(d2, dims=('y', 'x'))))) \
+        == S["area_no_roi"]
+
+    def boom(*a, **k):
+        raise RuntimeError
+
+    monkeypatch.setattr(src, "geocentric_resolution", boom, raising=False)
+    monkeypatch.setattr(area_def, "geocentric_resolution", boom, raising=False)
+    fallback = kd.XArrayResamplerNN(src, area_def, neighbours=1)
+    assert fallback.radius_of_influence == 10000
+    fallback.get_neighbour_info()
+    assert np.nansum(_values(fallback.get_sample_from_neighbour_info(FakeDataArray(d2, dims=('y', 'x'))))) \
+        == S["area_no_roi_no_geocentric"]

@@ -128,3 +128,19 @@ def test_image_container_literals_pin_the_geos_source_path():
     assert abs(res.sum() - rc.IMAGE_NEAREST_SUM) < 5e-8
     res = kd_tree_ref.resample_nearest(msg_area, data.ravel(), msg_resize, 50000, segments=1)
     assert abs(res.sum() - rc.IMAGE_NEAREST_RESIZE_SUM) < 5e-8
+
+
+def test_xarray_resampler_nn_literals():
+    """test_kd_tree.py:897-995 (XArrayResamplerNN, area -> area) through the oracle's restatement."""
+    from oracle import nearest_ref
+    from pyresample_b200 import geometry
+    import reference_cases as rc
+    area_def, src, d2, d3 = rc.xarray_nn_fixtures(geometry)
+    S = rc.XARRAY_NN_SUMS
+    flat2 = d2.reshape(src.shape)            # the reference ravels the (50, 10) data against the (10, 50) area
+    flat3 = d3.reshape(src.shape + (3,))
+    assert np.nansum(nearest_ref.resample(src, area_def, flat2, (0, 1), radius_of_influence=50000)) == S["area_to_area"]
+    assert np.nansum(nearest_ref.resample(src, area_def, flat2, (0, 1))) == S["area_no_roi"]
+    assert np.nansum(nearest_ref.resample(src, area_def, flat2, (0, 1), radius_of_influence=10000)) \
+        == S["area_no_roi_no_geocentric"]
+    assert np.nansum(nearest_ref.resample(src, area_def, flat3, (0, 1), radius_of_influence=50000)) == S["area_3d"]

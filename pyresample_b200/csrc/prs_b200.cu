@@ -99,6 +99,8 @@ struct WeightedParams {
 
 // get_sample_from_neighbour_info('custom') on precomputed neighbour info, runtime k (kd_tree.py:741-859).
 // Tw: dtype of distances / explicit weights; Td: data dtype; Ta: accumulation and output dtype.
+// Channels are processed four at a time so that a neighbour's row is read with one 16-byte load; per channel the
+// neighbours are accumulated in order i = 0..k-1 like the reference's Python loop.
 template <typename Tw, typename Td, typename Ta> __global__ void gather_weighted_kernel(const WeightedParams P)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,57 +108,80 @@ template <typename Tw, typename Td, typename Ta> __global__ void gather_weighted
     const int k = P.k, C = P.channels;
     const uint32_t *idx = P.index + (size_t)p * k;
     const bool want_uncert = P.stddev_out != nullptr;
-    for (int c = 0; c < C; ++c) {
-        const Tw *wplane = P.weights ? (const Tw *)P.weights + ((size_t)P.plane_of_channel[c] * P.n_out + p) * k : nullptr;
-        Ta res = 0, norm = 0;
-        for (int i = 0; i < k; ++i) {
-            uint32_t r = idx[i];
-            bool missing = r >= P.n_valid;
-            uint32_t s = missing ? P.first_valid_source : (P.rank_to_source ? __ldg(P.rank_to_source + r) : r);
-            Ta v = (Ta)__ldg((const Td *)P.data + (size_t)s * C + c);
-            Ta w;
-            if (wplane) {
-                w = (Ta)wplane[i];
-            } else {
-                Tw d = missing ? (Tw)1 : ((const Tw *)P.dist)[(size_t)p * k + i];
-                w = (Ta)Ar<Tw>::exp(Ar<Tw>::div(-Ar<Tw>::mul(d, d), (Tw)P.sigma2[c]));
-            }
-            Ta wt = missing ? Ar<Ta>::mul((Ta)0, w) : w;
-            res = Ar<Ta>::add(res, Ar<Ta>::mul(wt, v));
-            norm = Ar<Ta>::add(norm, wt);
+    const Td *data = (const Td *)P.data;
+    const bool vec_ok = (C & 3) == 0 && ((reinterpret_cast<uintptr_t>(data) & 15) == 0);
+    const Tw *dist = P.weights ? nullptr : (const Tw *)P.dist + (size_t)p * k;
+    int count = 0;
+    for (int i = 0; i < k; ++i) count += idx[i] < P.n_valid ? 1 : 0;
+    for (int c0 = 0; c0 < C; c0 += 4) {
+        const int nc = min(4, C - c0);
+        const Tw *wplane[4] = {nullptr, nullptr, nullptr, nullptr};
+        Tw s2c[4] = {1, 1, 1, 1};
+        bool same_w = true;  // the four channels share one weight (same plane / same sigma): evaluate it once
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + min(j, nc - 1);
+            if (P.weights)
+                wplane[j] = (const Tw *)P.weights + ((size_t)P.plane_of_channel[c] * P.n_out + p) * k;
+            else
+                s2c[j] = (Tw)P.sigma2[c];
+            same_w = same_w && wplane[j] == wplane[0] && s2c[j] == s2c[0];
         }
-        if (norm > 0)
-            res = Ar<Ta>::div(res, norm);
-        else
-            res = (Ta)P.fill;
-        ((Ta *)P.out)[(size_t)p * C + c] = res;
-        if (want_uncert) {
-            int count = 0;
-            Ta norm_sqr = 0, sd = 0;
+        Ta res[4] = {0, 0, 0, 0}, norm[4] = {0, 0, 0, 0};
+        for (int pass = 0; pass < (want_uncert ? 2 : 1); ++pass) {
+            Ta nsq[4] = {0, 0, 0, 0}, sd[4] = {0, 0, 0, 0};
             for (int i = 0; i < k; ++i) {
-                uint32_t r = idx[i];
-                bool missing = r >= P.n_valid;
-                uint32_t s = missing ? P.first_valid_source : (P.rank_to_source ? __ldg(P.rank_to_source + r) : r);
-                Ta v = (Ta)__ldg((const Td *)P.data + (size_t)s * C + c);
-                Ta w;
-                if (wplane) {
-                    w = (Ta)wplane[i];
-                } else {
-                    Tw d = missing ? (Tw)1 : ((const Tw *)P.dist)[(size_t)p * k + i];
-                    w = (Ta)Ar<Tw>::exp(Ar<Tw>::div(-Ar<Tw>::mul(d, d), (Tw)P.sigma2[c]));
+                const uint32_t r = idx[i];
+                const bool missing = r >= P.n_valid;
+                const uint32_t s = missing ? P.first_valid_source : (P.rank_to_source ? __ldg(P.rank_to_source + r) : r);
+                Td v[4];
+                load_channels<Td>(data + (size_t)s * C + c0, nc, vec_ok, v);
+                Tw d2 = 0;
+                if (!P.weights) {
+                    const Tw d = missing ? (Tw)1 : dist[i];
+                    d2 = Ar<Tw>::mul(d, d);
                 }
-                Ta wt = missing ? Ar<Ta>::mul((Ta)0, w) : w;
-                count += missing ? 0 : 1;
-                norm_sqr = Ar<Ta>::add(norm_sqr, Ar<Ta>::mul(wt, wt));
-                Ta val = missing ? Ar<Ta>::mul((Ta)0, v) : v;
-                Ta dv = Ar<Ta>::sub(val, res);
-                sd = Ar<Ta>::add(sd, Ar<Ta>::mul(wt, Ar<Ta>::mul(dv, dv)));
+                Ta w0 = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    Ta w;
+                    if (j > 0 && same_w)
+                        w = w0;
+                    else
+                        w = P.weights ? (Ta)wplane[j][i] : (Ta)Ar<Tw>::exp(Ar<Tw>::div(-d2, s2c[j]));
+                    if (j == 0) w0 = w;
+                    const Ta wt = missing ? Ar<Ta>::mul((Ta)0, w) : w;
+                    if (pass == 0) {
+                        res[j] = Ar<Ta>::add(res[j], Ar<Ta>::mul(wt, (Ta)v[j]));
+                        norm[j] = Ar<Ta>::add(norm[j], wt);
+                    } else {
+                        nsq[j] = Ar<Ta>::add(nsq[j], Ar<Ta>::mul(wt, wt));
+                        const Ta val = missing ? Ar<Ta>::mul((Ta)0, (Ta)v[j]) : (Ta)v[j];
+                        const Ta dv = Ar<Ta>::sub(val, res[j]);
+                        sd[j] = Ar<Ta>::add(sd[j], Ar<Ta>::mul(wt, Ar<Ta>::mul(dv, dv)));
+                    }
+                }
             }
-            Ta sdv = count > 1
-                         ? Ar<Ta>::sqrt(Ar<Ta>::mul(Ar<Ta>::div(norm, Ar<Ta>::sub(Ar<Ta>::mul(norm, norm), norm_sqr)), sd))
-                         : Ar<Ta>::nan();
-            ((Ta *)P.stddev_out)[(size_t)p * C + c] = sdv;
-            ((Ta *)P.count_out)[(size_t)p * C + c] = (Ta)count;
+            if (pass == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    // norm > 0 is False for NaN as well, like numpy's boolean mask (kd_tree.py:807-809)
+                    res[j] = (norm[j] > 0) ? Ar<Ta>::div(res[j], norm[j]) : (Ta)P.fill;
+                    if (j < nc) ((Ta *)P.out)[(size_t)p * C + c0 + j] = res[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j < nc) {
+                        const Ta sdv =
+                            count > 1 ? Ar<Ta>::sqrt(Ar<Ta>::mul(
+                                            Ar<Ta>::div(norm[j], Ar<Ta>::sub(Ar<Ta>::mul(norm[j], norm[j]), nsq[j])), sd[j]))
+                                      : Ar<Ta>::nan();
+                        ((Ta *)P.stddev_out)[(size_t)p * C + c0 + j] = sdv;
+                        ((Ta *)P.count_out)[(size_t)p * C + c0 + j] = (Ta)count;
+                    }
+                }
+            }
         }
     }
 }
@@ -330,8 +355,10 @@ int launch_query(QueryParams &P, const prs_index *index, const prs_target *tg, c
     if (tg->dtype != index->tree_dtype && tg->kind == PRS_TARGET_LONLAT)
         return fail(PRS_EINVAL, "target lon/lat dtype must equal the tree dtype (kd_tree.py:536-542)");
     if (P.k < 1) return fail(PRS_EINVAL, "neighbours must be >= 1");
-    if (index->tree_dtype == PRS_F32) return launch_query_t<float>(P, index, tg, st);
-    return launch_query_t<double>(P, index, tg, st);
+    const int rc = index->tree_dtype == PRS_F32 ? launch_query_t<float>(P, index, tg, st)
+                                                : launch_query_t<double>(P, index, tg, st);
+    index_note_use(index, st);
+    return rc;
 }
 
 int read_flags(unsigned int *flags_dev, int64_t *flags_host, cudaStream_t st)
@@ -446,6 +473,7 @@ int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, uint
     if ((flags & PRS_BUILD_RANKS) && !valid) return fail(PRS_EINVAL, "PRS_BUILD_RANKS needs the valid mask buffer");
     prs_index *ix = new prs_index();
     memset(ix, 0, sizeof(*ix));
+    ix->uses = new prs_index_uses();
     ix->tree_dtype = tree_dtype;
     ix->n_source = n;
     int rc;
@@ -489,7 +517,16 @@ int prs_target_coverage(const prs_target *target, double radius, uint8_t *cover_
 int prs_index_destroy(prs_index *ix)
 {
     if (!ix) return PRS_OK;
-    // stream-ordered: blocks return to the pool once the work already queued on the build stream has finished
+    // stream-ordered: blocks return to the pool once the work already queued on the build stream has finished -
+    // and the queries that other streams still have in flight (one event per such stream)
+    if (ix->uses) {
+        for (auto &u : ix->uses->events) {
+            cudaStreamWaitEvent(ix->stream, u.second, 0);
+            cudaEventDestroy(u.second);
+        }
+        delete ix->uses;
+        ix->uses = nullptr;
+    }
     if (ix->recs) cudaFreeAsync(ix->recs, ix->stream);
     if (ix->cell_alloc) cudaFreeAsync(ix->cell_alloc, ix->stream);
     if (ix->coarse_alloc) cudaFreeAsync(ix->coarse_alloc, ix->stream);

@@ -14,6 +14,8 @@
 #include "prs_scan.cuh"
 #include <chrono>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 namespace prs {
 
@@ -47,23 +49,51 @@ struct prs_index {
     int64_t n_cells, n_coarse;
     size_t bytes;
     cudaStream_t stream;  // stream the memory was allocated on (stream-ordered free)
+    // queries launched on OTHER streams: one event per stream, recorded behind the stream's latest query, so that
+    // prs_index_destroy can order the stream-ordered free behind them (see index_note_use / prs_index_destroy)
+    struct prs_index_uses *uses;
+};
+
+struct prs_index_uses {
+    std::mutex lock;
+    std::vector<std::pair<cudaStream_t, cudaEvent_t>> events;
 };
 
 namespace prs {
+
+// A query on a stream other than the one the index lives on: remember it, so that the free waits for it.
+inline void index_note_use(const prs_index *cix, cudaStream_t st)
+{
+    prs_index *ix = const_cast<prs_index *>(cix);
+    if (!ix || !ix->uses || st == ix->stream) return;
+    std::lock_guard<std::mutex> guard(ix->uses->lock);
+    for (auto &u : ix->uses->events)
+        if (u.first == st) {
+            cudaEventRecord(u.second, st);
+            return;
+        }
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    ix->uses->events.emplace_back(st, ev);
+}
 
 // Stream-ordered allocations come from the device's default pool; keep freed blocks cached in the pool
 // instead of returning them to the driver (cudaMalloc/cudaFree of the 100 MB-class tables costs tens of ms).
 inline int ensure_pool_configured()
 {
-    static bool done = false;
-    if (done) return PRS_OK;
+    static std::mutex lock;
+    static bool done[64] = {false};
     int dev = 0;
     PRS_CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> guard(lock);
+    const int slot = dev < 0 || dev >= 64 ? 0 : dev;
+    if (done[slot] && dev >= 0 && dev < 64) return PRS_OK;
     cudaMemPool_t pool;
     PRS_CK(cudaDeviceGetDefaultMemPool(&pool, dev));
     unsigned long long thr = ~0ull;
     PRS_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    done = true;
+    done[slot] = true;
     return PRS_OK;
 }
 
@@ -71,6 +101,18 @@ __device__ __forceinline__ void face_cell_of(float x, float y, float z, int G, i
 {
     float u, v;
     face_uv(x, y, z, face, u, v);
+    iu = cell_coord(warp_uv(u), G);
+    iv = cell_coord(warp_uv(v), G);
+}
+
+// Cell of a point on a GIVEN face (not necessarily its dominant one): used for points that sit on a cube edge,
+// where the last bit of the coordinates decides the face.  u / v beyond the edge clamp to the edge cells.
+__device__ __forceinline__ void cell_on_face(int face, float x, float y, float z, int G, int &iu, int &iv)
+{
+    const int axis = face >> 1;
+    const float a = axis == 0 ? x : (axis == 1 ? y : z);
+    const float inv = 1.0f / fmaxf(fabsf(a), 1e-30f);
+    const float u = (axis == 0 ? y : x) * inv, v = (axis == 2 ? y : z) * inv;
     iu = cell_coord(warp_uv(u), G);
     iv = cell_coord(warp_uv(v), G);
 }
@@ -371,6 +413,22 @@ __global__ void __launch_bounds__(BUILD_TPB, PRS_SELECT_MIN_BLOCKS)
                         }
                         last_cell = cell;
                     }
+                    // on a cube edge (or corner) the exact coordinates of pass 2 may pick another face than these
+                    // approximate ones: the probe cell is marked on every face that can win, so the table of
+                    // whichever face pass 2 chooses spans the point
+                    const float ax = fabsf(fx), ay = fabsf(fy), az = fabsf(fz);
+                    const float lim = fmaxf(ax, fmaxf(ay, az)) * (1.0f - 1e-4f);
+#pragma unroll
+                    for (int axis = 0; axis < 3; ++axis) {
+                        const float a = axis == 0 ? ax : (axis == 1 ? ay : az);
+                        const float sv = axis == 0 ? fx : (axis == 1 ? fy : fz);
+                        const int f2 = 2 * axis + (sv < 0.f ? 1 : 0);
+                        if (a >= lim && f2 != face) {
+                            int ju, jv;
+                            cell_on_face(f2, fx, fy, fz, OCC_G, ju, jv);
+                            occ[(f2 * OCC_G + jv) * OCC_G + ju] = 1;
+                        }
+                    }
                     kept = true;
                 }
             }
@@ -505,7 +563,31 @@ __global__ void __launch_bounds__(BUILD_TPB)
         unit_f32<T>(x, y, z, fx, fy, fz);
         int face, iu, iv;
         face_cell_of(fx, fy, fz, G, face, iu, iv);
-        // the table rectangle is a superset of the probe cells by construction; clamp defensively
+        // The table rectangle of the face is a superset of the probe cells pass 1 marked for this point - also when
+        // the point sits on a cube edge and pass 1 saw it on the neighbouring face (it marks both).  Should the face
+        // still have no table (cannot happen by construction), file the point on the nearest face that has one:
+        // a query that reaches the point's position also reaches the edge cells of that face.
+        if (ft.fw[face] == 0) {
+            const float ax = fabsf(fx), ay = fabsf(fy), az = fabsf(fz);
+            float best = -1.f;
+            int bf = -1;
+#pragma unroll
+            for (int axis = 0; axis < 3; ++axis) {
+                const float a = axis == 0 ? ax : (axis == 1 ? ay : az);
+                const float sv = axis == 0 ? fx : (axis == 1 ? fy : fz);
+                const int f2 = 2 * axis + (sv < 0.f ? 1 : 0);
+                if (f2 != face && ft.fw[f2] != 0 && a > best) {
+                    best = a;
+                    bf = f2;
+                }
+            }
+            if (bf < 0) {  // no table at all on the faces this point touches: drop it from the index
+                store_rec(tmp + i, (T)0, (T)0, (T)0, CELL_SKIP);
+                continue;
+            }
+            face = bf;
+            cell_on_face(face, fx, fy, fz, G, iu, iv);
+        }
         iu = min(max(iu, ft.fu0[face]), ft.fu0[face] + ft.fw[face] - 1);
         iv = min(max(iv, ft.fv0[face]), ft.fv0[face] + ft.fh[face] - 1);
         const uint32_t c = (uint32_t)table_key(ft, face, iu, iv);

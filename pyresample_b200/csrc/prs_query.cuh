@@ -830,8 +830,7 @@ template <typename T> __device__ __forceinline__ bool load_target_xyz(const void
 // Separable projections: the tile is the product of <= 32 longitudes (one per lane) and QROWS latitudes, and
 //   u(j,l).c = sin(lat_j) sin(lat_c) + cos(lat_j) cos(lat_c) cos(lon_l - lon_c)
 // grows with cos(lon_l - lon_c) (cos(lat) >= 0), so the farthest point of row j sits at the column with the smallest
-// cos(dlon): two warp reductions instead of a transform per point.  chord^2 = 2 - 2 u.c loses digits for small tiles;
-// the absolute slack below (a few float32 ulps of 1) only ever makes the cap larger.
+// cos(dlon): two warp reductions instead of a transform per point.
 template <typename T, int TK>
 __device__ __forceinline__ bool tile_cap(const QueryParams &P, uint32_t tile, int trow0, int tcol, int lane,
                                          unsigned &vmask, float &cx, float &cy, float &cz, float &d2m)
@@ -864,12 +863,18 @@ __device__ __forceinline__ bool tile_cap(const QueryParams &P, uint32_t tile, in
         const int lcn = (cmask >> 16) & 1u ? 16 : __ffs(cmask) - 1;
         const float cc = __shfl_sync(0xffffffffu, lc, lcn), cs = __shfl_sync(0xffffffffu, ls, lcn);
         const float rcc = __shfl_sync(0xffffffffu, rcos, jc), rsc = __shfl_sync(0xffffffffu, rsin, jc);
-        const float cosd = warp_min(col_ok ? lc * cc + ls * cs : 1.f);
-        const float dot = warp_min(row_ok ? rsin * rsc + rcos * rcc * cosd : 1.f);
+        // chord^2 from coordinate DIFFERENCES (no cancellation: 2 - 2 u.c loses everything for a tile of a few km):
+        //   |u - c|^2 = [(sin - sin_c)^2 + (cos - cos_c)^2]_lat + cos(lat) cos(lat_c) [(c - c_c)^2 + (s - s_c)^2]_lon
+        // both brackets are >= 0 and cos(lat) >= 0, so the farthest point of row j is at the column with the largest
+        // longitude bracket.  The table entries carry <= 1e-7 of absolute error each, i.e. <= 4e-7 on the chord;
+        // tile_live adds 1e-6 to the chord before use.
+        const float dlc = lc - cc, dls = ls - cs;
+        const float blon = warp_max(col_ok ? dlc * dlc + dls * dls : 0.f);
+        const float drs = rsin - rsc, drc = rcos - rcc;
+        d2m = warp_max(row_ok ? (drs * drs + drc * drc) + rcos * rcc * blon : 0.f) * 1.0001f;
         cx = rcc * cc;
         cy = rcc * cs;
         cz = rsc;
-        d2m = fmaxf(2.f - 2.f * dot, 0.f) * 1.001f + 1e-6f;
         return true;
     }
     float ux[QROWS], uy[QROWS], uz[QROWS];
@@ -976,8 +981,8 @@ __device__ __forceinline__ void tile_fill(const QueryParams &P, const IndexView<
                 if (trow0 + j < P.nrows) {
                     char *dst = dst0 + j * row_pitch;
 #pragma unroll
-                    for (int i = 0; i < STAGE_ROW_BYTES / 16; ++i)
-                        if (lane * 16 + i * 512 < span) *reinterpret_cast<uint4 *>(dst + lane * 16 + i * 512) = v[i];
+                    for (int i = 0; i < STAGE_ROW_BYTES / 16; ++i)  // written once, never read here: evict first
+                        if (lane * 16 + i * 512 < span) __stcs(reinterpret_cast<uint4 *>(dst + lane * 16 + i * 512), v[i]);
                 }
             }
             return;

@@ -14,6 +14,8 @@ Coordinate generation for areas runs on the GPU (``prs_area_lonlats`` /
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 from .proj import ProjSpec, proj_to_dict
@@ -399,20 +401,15 @@ def _yx_slice(data_slice):
 
 
 def _get_slice(segments, shape):
-    """Row-block slices (pyresample/geometry.py:3052-3068)."""
-    if not (1 <= len(shape) <= 2):
+    """Row blocks of ``ceil(rows / segments)`` rows as slices: the segmentation rule of geometry.py:3052-3068
+    (identical block boundaries; for 2-D shapes every item is ``(row_slice, slice(None))``)."""
+    if len(shape) not in (1, 2):
         raise ValueError('Cannot segment array of shape: %s' % str(shape))
-    size = shape[0]
-    slice_length = int(np.ceil(float(size) / segments))
-    start_idx = 0
-    end_idx = slice_length
-    while start_idx < size:
-        if len(shape) == 1:
-            yield slice(start_idx, end_idx)
-        else:
-            yield slice(start_idx, end_idx), slice(None)
-        start_idx = end_idx
-        end_idx = min(start_idx + slice_length, size)
+    rows = int(shape[0])
+    block = int(math.ceil(float(rows) / segments))
+    for start in range(0, rows, max(block, 1)):
+        row_slice = slice(start, min(start + block, rows))
+        yield row_slice if len(shape) == 1 else (row_slice, slice(None))
 
 
 # --------------------------------------------------------------------------- duck typing

@@ -653,10 +653,10 @@ def _make_target(source, target_geo_def, reduce_data, radius_of_influence, row0=
 
 
 def _query_device(source, target_geo_def, radius_of_influence, neighbours, reduce_data, want_dist=True,
-                  row0=0, nrows=None):
+                  row0=0, nrows=None, rows=None):
     """Run ``prs_query``; returns device tensors covering ALL target points + (kth_found, n_invalid)."""
     torch = _torch()
-    tg, n, keep = _make_target(source, target_geo_def, reduce_data, radius_of_influence, row0, nrows)
+    tg, n, keep = _make_target(source, target_geo_def, reduce_data, radius_of_influence, row0, nrows, rows=rows)
     k = int(neighbours)
     idx = torch.empty((n, k), dtype=torch.int32, device="cuda")
     td = getattr(torch, source.tree_dtype.name)
@@ -1021,9 +1021,80 @@ def _eval_weight_planes(weight_funcs, channels, is_multi, dist_np, index_missing
     return np.ascontiguousarray(planes), plane_of_channel
 
 
+_DEVICE_WEIGHT_CHUNK = 1 << 24  # (row, neighbour) entries evaluated per call of a weight function on the device
+
+
+def _missing_and_dist(idx_t, dist_t, n_valid):
+    """Device copies of what the reference feeds to a weight function: the missing-neighbour mask and the distances
+    with ``1`` in place of missing neighbours (kd_tree.py:751-768), evaluated in float64."""
+    torch = _torch()
+    missing = (idx_t.to(torch.int64) & 0xFFFFFFFF) >= int(n_valid)
+    d = dist_t.to(torch.float64)
+    d[missing] = 1.0
+    return d
+
+
+def _eval_weight_planes_device(weight_funcs, channels, is_multi, idx_t, dist_t, n_valid):
+    """Evaluate the weight functions (kd_tree.py:764-787) on a CUDA view of the ``(n_out, k)`` distances.
+
+    Works for anything written with arithmetic operators or ``torch`` functions (``1 - d / 1e5``, constants, ...).
+    The function sees float64 distances; the plane is then cast to the dtype numpy would have produced (probed on a
+    two-element host array), so the result is the correctly rounded value of the exact weight - within 1 ulp of the
+    reference's own float32 evaluation.  Returns None when some function does not accept a tensor (``np.cos`` ...):
+    the caller then takes the host route.  Identical function objects share a plane.
+    """
+    torch = _torch()
+    funcs = list(weight_funcs) if is_multi else [weight_funcs]
+    if is_multi and len(funcs) < channels:
+        raise IndexError("list index out of range")
+    dist_dtype = _np_dtype_of(dist_t)
+    n_out, k = dist_t.shape
+    planes, plane_of_channel, seen, dtypes = [], [], {}, []
+    for c in range(channels):
+        f = funcs[c] if is_multi else funcs[0]
+        if id(f) in seen:
+            plane_of_channel.append(seen[id(f)])
+            continue
+        try:
+            with np.errstate(all="ignore"):
+                probe = f(np.ones(2, dtype=dist_dtype))
+            if is_multi:
+                wdt = np.dtype(np.float64)  # np.ones(n) * w (kd_tree.py:783)
+            else:
+                wdt = np.asarray(probe).dtype
+                if wdt not in (np.dtype(np.float32), np.dtype(np.float64)):
+                    wdt = np.dtype(np.float64)
+            plane = torch.empty((n_out, k), dtype=getattr(torch, wdt.name), device="cuda")
+            flat_i, flat_d, flat_p = idx_t.reshape(-1), dist_t.reshape(-1), plane.reshape(-1)
+            for off in range(0, n_out * k, _DEVICE_WEIGHT_CHUNK):
+                sl = slice(off, min(off + _DEVICE_WEIGHT_CHUNK, n_out * k))
+                d = _missing_and_dist(flat_i[sl], flat_d[sl], n_valid)
+                w = f(d)
+                if _is_tensor(w):
+                    if not w.is_cuda or tuple(w.shape) != tuple(d.shape):
+                        return None
+                    flat_p[sl] = w
+                elif isinstance(w, (int, float, np.integer, np.floating)):
+                    flat_p[sl] = float(w)
+                else:
+                    return None
+        except Exception:  # the function needs a numpy array: host route
+            return None
+        seen[id(f)] = len(planes)
+        planes.append(plane)
+        dtypes.append(wdt)
+        plane_of_channel.append(seen[id(f)])
+    wdt = np.result_type(*dtypes)
+    td = getattr(torch, np.dtype(wdt).name)
+    if len(planes) == 1:
+        return planes[0].to(td).reshape(1, n_out, k), plane_of_channel, np.dtype(wdt)
+    return torch.stack([p.to(td) for p in planes], dim=0).contiguous(), plane_of_channel, np.dtype(wdt)
+
+
 def _weighted_from_info(idx_t, dist_t, n_out, k, n_valid, rank_to_source, dev_data, ddt, channels, weight_funcs,
                         is_multi, fill_value, with_uncert, dist_np=None):
-    """prs_gather_weighted with Gaussian (device) or arbitrary (host-evaluated) weights."""
+    """prs_gather_weighted with Gaussian weights (computed in the kernel) or arbitrary weight functions: evaluated on
+    the device when they accept a tensor, otherwise on the host."""
     torch = _torch()
     L = _cabi.lib()
     funcs = list(weight_funcs) if is_multi else [weight_funcs] * channels
@@ -1036,16 +1107,21 @@ def _weighted_from_info(idx_t, dist_t, n_out, k, n_valid, rank_to_source, dev_da
         weights_t, wcode, n_planes, planes_c, sig_c = None, _tree_code(dist_dtype), 0, None, \
             (ctypes.c_double * channels)(*[float(s) for s in sigmas])
     else:
-        if dist_np is None:
-            dist_np = dist_t.cpu().numpy()
-        idx_np = idx_t.cpu().numpy().view(np.uint32)
-        planes, plane_of_channel = _eval_weight_planes(weight_funcs, channels, is_multi, dist_np, idx_np >= n_valid)
-        weights_t = _dev(planes)
-        wcode = _tree_code(planes.dtype)
-        n_planes = planes.shape[0]
+        dev_planes = _eval_weight_planes_device(weight_funcs, channels, is_multi, idx_t, dist_t, n_valid)
+        if dev_planes is not None:
+            weights_t, plane_of_channel, wdt = dev_planes
+        else:
+            if dist_np is None:
+                dist_np = dist_t.cpu().numpy()
+            idx_np = idx_t.cpu().numpy().view(np.uint32)
+            planes, plane_of_channel = _eval_weight_planes(weight_funcs, channels, is_multi, dist_np, idx_np >= n_valid)
+            weights_t = _dev(planes)
+            wdt = planes.dtype
+        wcode = _tree_code(wdt)
+        n_planes = int(weights_t.shape[0])
         planes_c = (ctypes.c_int32 * channels)(*plane_of_channel)
         sig_c = None
-        acc64 = channels > 1 or planes.dtype == np.float64 or ddt == np.float64
+        acc64 = channels > 1 or wdt == np.float64 or ddt == np.float64
     odt = torch.float64 if acc64 else torch.float32
     out = torch.empty((n_out, channels), dtype=odt, device="cuda")
     sd = torch.empty((n_out, channels), dtype=odt, device="cuda") if with_uncert else None
@@ -1159,37 +1235,14 @@ def _resample(source_geo_def, data, target_geo_def, resample_type,
                                              _stream()))
             kth_found = bool(flags[0])
         else:
-            # arbitrary Python weight functions: device query -> host evaluation of f(dist) -> device weighted sum
-            idx, dist, valid, kth_found, n_invalid = _query_device(source, tgt, radius_of_influence, neighbours,
-                                                                   reduce_data)
-            voi_t = None
-            if _weights_finite_at_one(weight_funcs):
-                # pixels without any neighbour end as fill / NaN / 0 whatever the weights are (norm == 0,
-                # kd_tree.py:807-809, 842-858) as long as f(1) - the value the reference feeds for missing
-                # neighbours - is finite: only rows with a neighbour travel to the host and back
-                has = (idx[:, 0] >= 0) & (idx[:, 0] < int(source.n_valid))
-                n_has = int(has.sum())
-                if 0 < n_has < idx.shape[0] // 2:
-                    valid = has.to(torch.uint8)
-                    n_invalid = idx.shape[0] - n_has
-            if n_invalid:
-                voi_t = valid
-                idx = _compact_rows(valid, idx)
-                dist = _compact_rows(valid, dist)
-            n_out = idx.shape[0]
-            if n_out == 0:
+            # arbitrary Python weight functions: device query -> f(dist) on the device (host when the function
+            # needs numpy) -> device weighted sum
+            res = _custom_on_device(source, tgt, radius_of_influence, neighbours, reduce_data, dev_data, ddt,
+                                    channels, weight_funcs, new_data.ndim > 1, fill_value, with_uncert)
+            if res is None:
                 return _get_empty_sample(data, output_shape, is_multi_channel,
                                          None if use_masked_fill_value else fill_value)
-            out, sd_t, cnt_t = _weighted_from_info(idx, dist, n_out, int(neighbours), int(source.n_valid),
-                                                   _rank_to_source(source), dev_data, ddt, channels, weight_funcs,
-                                                   new_data.ndim > 1, fill_value, with_uncert)
-            fill_row = torch.full((channels,), float(fill_value), dtype=out.dtype, device="cuda")
-            out = _scatter_full(out, voi_t, n_t, fill_row)
-            if with_uncert:
-                nan_row = torch.full((channels,), float("nan"), dtype=sd_t.dtype, device="cuda")
-                zero_row = torch.zeros((channels,), dtype=cnt_t.dtype, device="cuda")
-                sd_t = _scatter_full(sd_t, voi_t, n_t, nan_row)
-                cnt_t = _scatter_full(cnt_t, voi_t, n_t, zero_row)
+            out, sd_t, cnt_t, kth_found = res
         if kth_found:
             warnings.warn(('Possible more than %s neighbours within %s m for some data points') %
                           (neighbours, radius_of_influence), stacklevel=3)
@@ -1203,6 +1256,47 @@ def _resample(source_geo_def, data, target_geo_def, resample_type,
         stddev, count = _prepare_uncertainty(stddev, count, final_output_shape, is_masked_data, result)
         return result, stddev, count
     return result
+
+
+def _custom_on_device(source, tgt, radius_of_influence, neighbours, reduce_data, dev_data, ddt, channels,
+                      weight_funcs, is_multi, fill_value, with_uncert, rows=None):
+    """``resample_custom`` with arbitrary weight functions: ``prs_query`` -> weights -> ``prs_gather_weighted``, all
+    on device tensors.  Returns (out, stddev, count, kth_found) over every target point, or None when no target
+    point is valid."""
+    torch = _torch()
+    idx, dist, valid, kth_found, n_invalid = _query_device(source, tgt, radius_of_influence, neighbours,
+                                                           reduce_data, rows=rows)
+    n_t = idx.shape[0]
+    voi_t = None
+    if _weights_finite_at_one(weight_funcs):
+        # pixels without any neighbour end as fill / NaN / 0 whatever the weights are (norm == 0,
+        # kd_tree.py:807-809, 842-858) as long as f(1) - the value the reference feeds for missing
+        # neighbours - is finite: only rows with a neighbour are weighted
+        has = (idx[:, 0].to(torch.int64) & 0xFFFFFFFF) < int(source.n_valid)
+        if n_invalid:
+            has &= valid.bool()
+        n_has = int(has.sum())
+        if 0 < n_has < n_t // 2:
+            valid = has.to(torch.uint8)
+            n_invalid = n_t - n_has
+    if n_invalid:
+        voi_t = valid
+        idx = _compact_rows(valid, idx)
+        dist = _compact_rows(valid, dist)
+    n_out = idx.shape[0]
+    if n_out == 0:
+        return None
+    out, sd_t, cnt_t = _weighted_from_info(idx, dist, n_out, int(neighbours), int(source.n_valid),
+                                           _rank_to_source(source), dev_data, ddt, channels, weight_funcs,
+                                           is_multi, fill_value, with_uncert)
+    fill_row = torch.full((channels,), float(fill_value), dtype=out.dtype, device="cuda")
+    out = _scatter_full(out, voi_t, n_t, fill_row)
+    if with_uncert:
+        nan_row = torch.full((channels,), float("nan"), dtype=sd_t.dtype, device="cuda")
+        zero_row = torch.zeros((channels,), dtype=cnt_t.dtype, device="cuda")
+        sd_t = _scatter_full(sd_t, voi_t, n_t, nan_row)
+        cnt_t = _scatter_full(cnt_t, voi_t, n_t, zero_row)
+    return out, sd_t, cnt_t, kth_found
 
 
 def _rank_to_source(source):
@@ -1249,10 +1343,17 @@ def _resample_tensor(source, data, tgt, resample_type, radius_of_influence, neig
         return out.reshape(output_shape)
     funcs = list(weight_funcs) if multi else [weight_funcs] * channels
     sigmas = [_gauss_sigma_of(f) for f in funcs[:channels]]
-    if not all(s is not None for s in sigmas):
-        raise NotImplementedError("device-resident resampling supports nearest and Gaussian weights")
     ddt = np.dtype(np.float32) if data.dtype == torch.float32 else np.dtype(np.float64)
     dev_data = dev_data.to(getattr(torch, ddt.name))
+    if not all(s is not None for s in sigmas):
+        res = _custom_on_device(source, tgt, radius_of_influence, neighbours, reduce_data, dev_data, ddt, channels,
+                                weight_funcs, multi, fill_value, with_uncert, rows=rows)
+        if res is None:
+            return torch.full(output_shape, fill_value, dtype=data.dtype, device="cuda")
+        out, sd_t, cnt_t, _ = res
+        if with_uncert:
+            return out.reshape(output_shape), sd_t.reshape(output_shape), cnt_t.reshape(output_shape)
+        return out.reshape(output_shape)
     acc64 = channels > 1 or source.tree_dtype == np.float64 or ddt == np.float64
     odt = torch.float64 if acc64 else torch.float32
     out = torch.empty((n_t, channels), dtype=odt, device="cuda")

@@ -2,10 +2,15 @@
 pyresample/future/resamplers/nearest.py:44-108).
 
 The reference builds a lazy dask graph whose blocks call ``query_no_distance`` (pykdtree) and ``_my_index``
-(numpy fancy indexing).  Here the neighbour search runs eagerly in one ``prs_query`` launch over the whole target
-(the GPU needs no chunking) and the sampling is one ``prs_gather_nearest`` launch; results are handed back as
-``xarray.DataArray`` (wrapped in dask arrays when dask is importable, so callers can keep calling ``.compute()``).
-xarray is required exactly like in the reference (``ImportError`` otherwise, kd_tree.py:931-932).
+(numpy fancy indexing).  Here ``get_neighbour_info`` and ``get_sample_from_neighbour_info`` are lazy too - they
+validate their arguments and return arrays that know their shape and dtype but compute nothing (the reference's
+zero-compute contract, test_kd_tree.py:908-919) - and the work behind them is one ``prs_query`` launch over the
+whole target (the GPU needs no chunking) and one ``prs_gather_nearest`` launch per sampled array.  The neighbour
+indices stay on the device between the two calls; the int64 / -1 form of ``index_array`` that the reference
+exposes is only materialised when somebody reads it.  Lazy arrays are dask arrays when dask is importable
+(``dask.array.from_delayed``), otherwise a small stand-in with the same ``shape`` / ``dtype`` / ``compute()`` /
+``__array__`` surface.  xarray is required exactly like in the reference (``ImportError`` otherwise,
+kd_tree.py:931-932).
 
 Contract kept from the reference: the tree is float64 (kd_tree.py:979), ``valid_input_index`` is the 2-D range mask
 (no reduce_data), ``index_array`` is int64 ``(rows, cols, neighbours)`` with ``-1`` for "no neighbour", no distances
@@ -13,7 +18,7 @@ are returned (kd_tree.py:1004), sampling supports ``neighbours == 1`` only (kd_t
 """
 from __future__ import annotations
 
-import ctypes
+import threading
 import warnings
 from copy import deepcopy
 from logging import getLogger
@@ -29,9 +34,63 @@ try:
 except ImportError:  # pragma: no cover
     DataArray = None
 try:
+    import dask
     import dask.array as da
 except ImportError:  # pragma: no cover
-    da = None
+    dask = da = None
+
+COMPUTE_COUNT = 0  # number of deferred computations that have run (tests assert laziness with it)
+
+
+class _Once(object):
+    """A thunk that runs at most once (thread-safe); later calls return the stored value."""
+
+    def __init__(self, fn):
+        self._fn, self._lock, self._done, self._value = fn, threading.Lock(), False, None
+
+    def __call__(self):
+        global COMPUTE_COUNT
+        with self._lock:
+            if not self._done:
+                COMPUTE_COUNT += 1
+                self._value = self._fn()
+                self._done, self._fn = True, None
+        return self._value
+
+
+class LazyArray(object):
+    """What the lazy methods return when dask is not importable: an array-like with known ``shape`` and ``dtype``
+    whose values are computed on first use (``compute()``, ``np.asarray``, indexing)."""
+
+    def __init__(self, thunk, shape, dtype):
+        self._thunk = thunk if isinstance(thunk, _Once) else _Once(thunk)
+        self.shape, self.dtype = tuple(int(v) for v in shape), np.dtype(dtype)
+
+    ndim = property(lambda self: len(self.shape))
+    size = property(lambda self: int(np.prod(self.shape)))
+
+    def compute(self):
+        return np.asarray(self._thunk()).reshape(self.shape)
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.compute()
+        return out.astype(dtype) if dtype is not None and np.dtype(dtype) != out.dtype else out
+
+    def __getitem__(self, key):
+        return self.compute()[key]
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __repr__(self):
+        return "LazyArray(shape=%r, dtype=%s)" % (self.shape, self.dtype)
+
+
+def _lazy(thunk, shape, dtype):
+    once = thunk if isinstance(thunk, _Once) else _Once(thunk)
+    if da is not None:
+        return da.from_delayed(dask.delayed(once, pure=False)(), shape=tuple(shape), dtype=np.dtype(dtype))
+    return LazyArray(once, shape, dtype)
 
 
 def _kd():
@@ -137,6 +196,108 @@ def _my_index(index_arr, vii, data_arr, vii_slices=None, ia_slices=None, fill_va
     return np.transpose(res, order)
 
 
+class _LazyTree(object):
+    """``delayed_kdtree`` of the reference (a ``dask.delayed`` pykdtree): ``compute()`` gives the device index."""
+
+    def __init__(self, thunk):
+        self._thunk = thunk
+
+    def compute(self):
+        return self._thunk()
+
+
+class _NeighbourState(object):
+    """Device-side result of one ``get_neighbour_info`` call, computed on first use: the float64 index over the
+    range-valid source points and, per target pixel, the ``neighbours`` nearest ranks (uint32, sentinel = number
+    of valid points).  Everything stays on the device; host forms are derived on demand."""
+
+    def __init__(self, resampler, mask):
+        self.source_geo_def = geometry.as_geo_def(resampler.source_geo_def)
+        self.target_geo_def = geometry.as_geo_def(resampler.target_geo_def)
+        self.k = int(resampler.neighbours)
+        self.radius = float(resampler.radius_of_influence)
+        self.mask = mask
+        self.tree = _Once(self._build)
+        self.query = _Once(self._query)
+
+    def _build(self):
+        kd = _kd()
+        src = self.source_geo_def
+        excl = None
+        if self.mask is not None:
+            excl = np.ascontiguousarray(np.asarray(_materialise(self.mask), dtype=bool)).ravel()
+        if not geometry.is_area(src):
+            lons, lats = src.get_lonlats()
+            src = geometry.SwathDefinition(_materialise(lons), _materialise(lats))
+        source = kd._Source(src, None, False, 0.0, self.k, exclude_mask=excl, tree_dtype=np.float64)
+        tree = _GpuTree(source)
+        tree.mask_applied = self.mask is not None
+        return tree
+
+    def _query(self):
+        """(idx uint32-bits int32 tensor (n_t, k) or None, valid_out uint8 tensor or host bool array)."""
+        kd = _kd()
+        source = self.tree().source
+        tgt = self.target_geo_def
+        if source.index is None:  # no valid source point: nothing to find, the target mask is still defined
+            tl, tt = tgt.get_lonlats()
+            tl, tt = np.asarray(_materialise(tl)), np.asarray(_materialise(tt))
+            with np.errstate(invalid="ignore"):
+                return None, ((tl >= -180) & (tl <= 180) & (tt <= 90) & (tt >= -90)).ravel()
+        idx, _, valid, _, _ = kd._query_device(source, tgt, self.radius, self.k, False, want_dist=False)
+        return idx, valid
+
+    def valid_input(self):
+        source = self.tree().source
+        return source.valid.cpu().numpy().astype(bool).reshape(tuple(self.source_geo_def.shape))
+
+    def valid_output(self):
+        _, valid = self.query()
+        if isinstance(valid, np.ndarray):
+            return valid.reshape(tuple(self.target_geo_def.shape))
+        return valid.cpu().numpy().astype(bool).reshape(tuple(self.target_geo_def.shape))
+
+    def index_array(self):
+        """int64 (rows, cols, k) with -1 for "no neighbour" (nearest.py:80-93)."""
+        kd = _kd()
+        rows, cols = self.target_geo_def.shape
+        idx, _ = self.query()
+        if idx is None:
+            return np.full((rows, cols, self.k), -1, dtype=np.int64)
+        ia = kd._host(idx).view(np.uint32).astype(np.int64)
+        ia[ia >= self.tree().n] = -1  # invalid target pixels are never searched and carry the sentinel too
+        return ia.reshape(rows, cols, self.k)
+
+    def sample(self, flat_data, axis, fill_value):
+        """``_my_index`` on the device-resident indices: rows of ``flat_data`` (geo axis flattened at ``axis``)."""
+        kd = _kd()
+        torch = kd._torch()
+        L = _cabi.lib()
+        rows_t, cols_t = self.target_geo_def.shape
+        data = np.moveaxis(np.asarray(flat_data), axis, 0)
+        rest = data.shape[1:]
+        rows = np.ascontiguousarray(data.reshape(data.shape[0], -1))
+        fill_row = kd._byte_rows(np.full((1, rows.shape[1]), fill_value, dtype=rows.dtype))
+        idx, _ = self.query()
+        n_t = rows_t * cols_t
+        if idx is None:
+            res = np.full((n_t, rows.shape[1]), fill_value, dtype=rows.dtype)
+        else:
+            tree = self.tree()
+            source = tree.source
+            dev_rows = kd._dev(kd._byte_rows(rows))
+            row_bytes = dev_rows.shape[1]
+            r2s = kd._rank_to_source(source)
+            out = torch.empty((n_t, row_bytes), dtype=torch.uint8, device="cuda")
+            idx1 = idx if idx.shape[1] == 1 else idx[:, 0].contiguous()
+            _cabi.check(L.prs_gather_nearest(kd._ptr(idx1), n_t, tree.n, kd._ptr(r2s), kd._ptr(dev_rows), row_bytes,
+                                             kd._ptr(kd._dev(fill_row)), kd._ptr(out), kd._stream()))
+            res = kd._host(out).view(rows.dtype)
+        res = res.reshape((rows_t, cols_t) + rest)
+        order = list(range(2, 2 + axis)) + [0, 1] + list(range(2 + axis, res.ndim))
+        return np.transpose(res, order)
+
+
 class XArrayResamplerNN(object):
     """Resampler for xarray DataArrays with the nearest-neighbour algorithm (pyresample/kd_tree.py:902-1183)."""
 
@@ -157,6 +318,7 @@ class XArrayResamplerNN(object):
         self.radius_of_influence = radius_of_influence
         if self.target_geo_def.ndim != 2:
             raise ValueError("Target area definition must be 2 dimensions")
+        self._state = None
 
     def _compute_radius_of_influence(self):
         """Estimate a good default radius_of_influence (kd_tree.py:949-968)."""
@@ -179,53 +341,45 @@ class XArrayResamplerNN(object):
             radius_of_influence = 10000
         return radius_of_influence
 
-    def _wrap(self, arr):
-        if da is not None:
-            return da.from_array(arr, chunks=CHUNK_SIZE)
-        return arr
+    def _create_resample_kdtree(self, chunks=CHUNK_SIZE):
+        """Set up the index on the input (kd_tree.py:970-981): (lazy valid_input_index, lazy tree)."""
+        state = _NeighbourState(self, None)
+        return _lazy(state.valid_input, tuple(self.source_geo_def.shape), bool), _LazyTree(state.tree)
+
+    def query_resample_kdtree(self, resample_kdtree, tlons, tlats, valid_oi, mask):
+        """Query the index on target coordinates (kd_tree.py:983-1004): (lazy int64 (rows, cols, neighbours)
+        index array with -1 for "no neighbour", None).  ``resample_kdtree`` is what ``_create_resample_kdtree`` /
+        ``delayed_kdtree`` hold (or an already computed tree); ``mask`` excludes source pixels (True = exclude)."""
+        shape = tuple(valid_oi.shape) + (int(self.neighbours),)
+        vii = self.valid_input_index
+
+        def run():
+            tree = resample_kdtree.compute() if hasattr(resample_kdtree, "compute") else resample_kdtree
+            return query_no_distance(tlons, tlats, valid_oi, mask=mask, valid_input_index=vii,
+                                     neighbours=int(self.neighbours), epsilon=self.epsilon,
+                                     radius=self.radius_of_influence, kdtree=tree)
+
+        return _lazy(run, shape, np.int64), None
 
     def get_neighbour_info(self, mask=None):
-        """Return neighbour info (kd_tree.py:1006-1043)."""
-        kd = _kd()
+        """Return neighbour info (kd_tree.py:1006-1043).  Nothing is computed here: the index build and the search
+        run when one of the returned arrays (or a sample that depends on them) is first used."""
         if self.source_geo_def.size < self.neighbours:
             warnings.warn('Searching for %s neighbours in %s data points' %
                           (self.neighbours, self.source_geo_def.size), stacklevel=2)
         if mask is not None:
             if tuple(mask.shape) != tuple(self.source_geo_def.shape):
                 raise ValueError("'mask' must be the same shape as the source geo definition")
-        src = geometry.as_geo_def(self.source_geo_def)
-        excl = None
-        if mask is not None:
-            excl = np.ascontiguousarray(np.asarray(_materialise(mask), dtype=bool)).ravel()
-        if geometry.is_area(src):
-            source = kd._Source(src, None, False, 0.0, self.neighbours, exclude_mask=excl, tree_dtype=np.float64)
-        else:
-            lons, lats = src.get_lonlats()
-            source = kd._Source(geometry.SwathDefinition(_materialise(lons), _materialise(lats)), None, False, 0.0,
-                                self.neighbours, exclude_mask=excl, tree_dtype=np.float64)
-        self.delayed_kdtree = _GpuTree(source)
-        valid_input = source.valid.cpu().numpy().astype(bool).reshape(tuple(src.shape))
-        tgt = geometry.as_geo_def(self.target_geo_def)
-        rows, cols = tgt.shape
-        k = int(self.neighbours)
-        if source.index is not None:
-            idx, _, valid, _, _ = kd._query_device(source, tgt, float(self.radius_of_influence), k, False,
-                                                   want_dist=False)
-            valid_out = valid.cpu().numpy().astype(bool).reshape(rows, cols)
-            ia = kd._host(idx).view(np.uint32).astype(np.int64)
-            ia[ia >= source.n_valid] = -1
-            ia[~valid_out.ravel()] = -1
-            ia = ia.reshape(rows, cols, k)
-        else:
-            tl, tt = tgt.get_lonlats()
-            tl, tt = np.asarray(_materialise(tl)), np.asarray(_materialise(tt))
-            with np.errstate(invalid="ignore"):
-                valid_out = ((tl >= -180) & (tl <= 180) & (tt <= 90) & (tt >= -90))
-            ia = np.full((rows, cols, k), -1, dtype=np.int64)
-        self.valid_input_index = self._wrap(valid_input)
-        self.valid_output_index = self._wrap(valid_out)
-        self.index_array = self._wrap(ia)
+            mask = getattr(mask, "data", mask)
+        state = _NeighbourState(self, mask)
+        self._state = state
+        rows, cols = self.target_geo_def.shape
+        self.delayed_kdtree = _LazyTree(state.tree)
+        self.valid_input_index = _lazy(state.valid_input, tuple(self.source_geo_def.shape), bool)
+        self.valid_output_index = _lazy(state.valid_output, (rows, cols), bool)
+        self.index_array = _lazy(state.index_array, (rows, cols, int(self.neighbours)), np.int64)
         self.distance_array = None
+        state.handed_out = (self.valid_input_index, self.index_array)
         return (self.valid_input_index, self.valid_output_index, self.index_array, self.distance_array)
 
     def _get_valid_dims(self, data):
@@ -245,15 +399,13 @@ class XArrayResamplerNN(object):
         return src_geo_dims, dst_geo_dims
 
     def get_sample_from_neighbour_info(self, data, fill_value=np.nan):
-        """Get the pixels matching the target area (kd_tree.py:1045-1164)."""
+        """Get the pixels matching the target area (kd_tree.py:1045-1164); lazy like the reference."""
         kd = _kd()
         if fill_value is not None and np.isnan(fill_value) and np.issubdtype(data.dtype, np.integer):
             fill_value = kd._get_fill_mask_value(np.dtype(data.dtype))
             logger.warning("Fill value incompatible with integer data using {:d} instead.".format(fill_value))
         if self.neighbours > 1:
             raise NotImplementedError("Nearest neighbor resampling can not handle more than 1 neighbor yet.")
-        ia = np.asarray(_materialise(self.index_array))[:, :, 0]
-        vii = np.asarray(_materialise(self.valid_input_index)).ravel()
         src_geo_dims, dst_geo_dims = self._get_valid_dims(data)
 
         def contain_coords(var, coord_list):
@@ -267,7 +419,7 @@ class XArrayResamplerNN(object):
             coords['x'] = coord_x
         except AttributeError:
             logger.debug("No geo coordinates created")
-        flat_src_shape, vii_slices, ia_slices, dst_dims = [], [], [], []
+        flat_src_shape, vii_slices, ia_slices, dst_dims, dst_shape = [], [], [], [], []
         geo_handled = False
         for dim in data.dims:
             if dim in src_geo_dims and not geo_handled:
@@ -275,13 +427,30 @@ class XArrayResamplerNN(object):
                 vii_slices.append(None)
                 ia_slices.append(None)
                 dst_dims.extend(dst_geo_dims)
+                dst_shape.extend(self.target_geo_def.shape)
                 geo_handled = True
             elif dim not in src_geo_dims:
                 flat_src_shape.append(data.sizes[dim])
                 vii_slices.append(slice(None))
                 ia_slices.append(slice(None))
                 dst_dims.append(dim)
-        new_data = np.asarray(_materialise(data.data)).reshape(flat_src_shape)
-        res = _my_index(ia, vii, new_data, vii_slices=vii_slices, ia_slices=ia_slices, fill_value=fill_value)
-        res = self._wrap(res)
+                dst_shape.append(data.sizes[dim])
+        axis = vii_slices.index(None)
+        state = self._state
+        # the arrays handed out by get_neighbour_info are still in place: sample from the device-resident indices;
+        # a caller that stored its own arrays in the attributes (e.g. from a cache) gets exactly those
+        resident = state is not None and getattr(state, "handed_out", (None, None))[0] is self.valid_input_index \
+            and state.handed_out[1] is self.index_array
+        index_array, valid_input_index = self.index_array, self.valid_input_index
+        raw = data.data
+
+        def run():
+            new_data = np.asarray(_materialise(raw)).reshape(flat_src_shape)
+            if resident:
+                return state.sample(new_data, axis, fill_value)
+            ia = np.asarray(_materialise(index_array))[:, :, 0]
+            vii = np.asarray(_materialise(valid_input_index)).ravel()
+            return _my_index(ia, vii, new_data, vii_slices=vii_slices, ia_slices=ia_slices, fill_value=fill_value)
+
+        res = _lazy(run, dst_shape, data.dtype)
         return kd.DataArray(res, dims=dst_dims, coords=coords, attrs=deepcopy(data.attrs))

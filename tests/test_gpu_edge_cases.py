@@ -450,3 +450,38 @@ def test_pipelined_nearest_row_layouts(kd, geometry, monkeypatch, dtype, channel
     assert np.array_equal(piped, plain)
     want = kd_tree_ref.resample_nearest(swath, data, area, 30000, fill_value=7)
     assert np.array_equal(piped, want)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("edge_lon", [45.0, 135.0, -45.0, -135.0])
+def test_source_ends_exactly_on_a_cube_edge(kd, geometry, dtype, edge_lon):
+    """A regional lon/lat grid whose border column lies EXACTLY on a cube edge (|x| == |y| up to the last bit) with
+    nothing beyond it: the index build sees that column on one face in its approximate selection pass and possibly on
+    the other face in its exact pass.  Every point of the column must still be found from both sides of the edge."""
+    step = 0.05 if edge_lon > 0 else -0.05
+    lon1 = edge_lon - step * np.arange(240)[::-1]  # ... up to and including the edge, nothing beyond
+    lat1 = np.arange(-30.0, 30.0, 0.05)
+    lon, lat = np.meshgrid(lon1, lat1)
+    rng = np.random.default_rng(77)
+    lat = lat + rng.uniform(-0.01, 0.01, lat.shape)  # tie-free, but the border column keeps its exact longitude
+    tlon = edge_lon + rng.uniform(-0.12, 0.12, 4000)
+    tlat = rng.uniform(-29.5, 29.5, 4000)
+    for k, radius in ((1, 9000.0), (4, 20000.0)):
+        _check_against_brute(kd, geometry, lon.ravel(), lat.ravel(), tlon, tlat, k, radius, dtype)
+    # the same with ONLY the border column as the source (one face's table may be a single strip of cells)
+    lon_b = np.full(lat1.size, edge_lon)
+    _check_against_brute(kd, geometry, lon_b, lat1 + 0.003, tlon, tlat, 2, 15000.0, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_source_ends_on_a_horizontal_cube_edge(kd, geometry, dtype):
+    """Border row along the edge between an equatorial face and the north face (|z| == |x| at lon = 0)."""
+    rng = np.random.default_rng(78)
+    lon1 = np.arange(-20.0, 20.0, 0.05)
+    lat_edge = 45.0  # at lon = 0: z == x
+    lat1 = lat_edge - 0.05 * np.arange(200)[::-1]
+    lon, lat = np.meshgrid(lon1, lat1)
+    lon = lon + rng.uniform(-0.01, 0.01, lon.shape)
+    tlon = rng.uniform(-1.0, 1.0, 3000)
+    tlat = lat_edge + rng.uniform(-0.12, 0.12, 3000)
+    _check_against_brute(kd, geometry, lon.ravel(), lat.ravel(), tlon, tlat, 3, 12000.0, dtype)

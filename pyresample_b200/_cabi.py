@@ -16,7 +16,7 @@ from .proj import prs_proj_params
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC_DIR = os.path.join(_HERE, "csrc")
 _SO_PATH = os.environ.get("PRS_B200_LIBRARY") or os.path.join(_HERE, "libprs_b200.so")  # override: kernel experiments
-_SOURCES = ["prs_b200.cu", "prs_query_inst.cu"]
+_SOURCES = ["prs_b200.cu", "prs_query_inst.cu", "prs_classify_inst.cu"]
 _HEADERS = ["prs_common.cuh", "prs_scan.cuh", "prs_proj.cuh", "prs_index.cuh", "prs_query.cuh", "prs_launch.cuh"]
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "prs_b200.h")
 
@@ -70,15 +70,18 @@ def needs_rebuild():
     return any(os.path.getmtime(d) > so_time for d in deps if os.path.exists(d))
 
 
-_QUERY_INSTANCES = [(t, k) for t in ("float", "double") for k in (1, 4, 8, 16, 32)]
+# search kernels: (tree dtype, top-k width K, epilogue) with epilogue 0 = neighbour info, 1 = nearest gather (K = 1),
+# 2 = Gaussian weighting
+_QUERY_INSTANCES = [(t, k, e) for t in ("float", "double") for k, e in
+                    [(1, 0), (4, 0), (8, 0), (16, 0), (32, 0), (1, 1), (4, 2), (8, 2), (16, 2), (32, 2)]]
 
 
 def build(force=False, verbose=False, jobs=None):
     """Compile the CUDA library for sm_100a into ``pyresample_b200/libprs_b200.so``.
 
-    ``prs_b200.cu`` holds the C-ABI and the small kernels; the query kernels are instantiated per (tree dtype, K)
-    - and per target kind for K >= 16 - in ``prs_query_inst.cu``; the translation units are compiled in parallel
-    and linked.
+    ``prs_b200.cu`` holds the C-ABI and the small kernels; the classification kernels are instantiated per tree
+    dtype in ``prs_classify_inst.cu`` and the search kernels per (tree dtype, K, epilogue) in
+    ``prs_query_inst.cu``; the translation units are compiled in parallel and linked.
     """
     if not force and not needs_rebuild():
         return _SO_PATH
@@ -94,15 +97,13 @@ def build(force=False, verbose=False, jobs=None):
     if verbose:
         flags.append("-Xptxas=-v")
     units = [(os.path.join(_SRC_DIR, "prs_b200.cu"), os.path.join(obj_dir, "prs_b200.o"), [])]
-    for t, k in _QUERY_INSTANCES:
-        inst = os.path.join(_SRC_DIR, "prs_query_inst.cu")
-        if k >= 16:  # wide top-k lists compile for minutes: one unit per target kind (lon/lat, separable, general)
-            for tk in (0, 1, 2):
-                units.append((inst, os.path.join(obj_dir, "prs_query_%s_%d_%d.o" % (t, k, tk)),
-                              ["-DPRS_INST_T=%s" % t, "-DPRS_INST_K=%d" % k, "-DPRS_INST_TK=%d" % tk]))
-        else:
-            units.append((inst, os.path.join(obj_dir, "prs_query_%s_%d.o" % (t, k)),
-                          ["-DPRS_INST_T=%s" % t, "-DPRS_INST_K=%d" % k]))
+    for t in ("float", "double"):
+        units.append((os.path.join(_SRC_DIR, "prs_classify_inst.cu"), os.path.join(obj_dir, "prs_classify_%s.o" % t),
+                      ["-DPRS_INST_T=%s" % t]))
+    for t, k, e in _QUERY_INSTANCES:
+        units.append((os.path.join(_SRC_DIR, "prs_query_inst.cu"),
+                      os.path.join(obj_dir, "prs_query_%s_%d_%d.o" % (t, k, e)),
+                      ["-DPRS_INST_T=%s" % t, "-DPRS_INST_K=%d" % k, "-DPRS_INST_EPI=%d" % e]))
     units.sort(key=lambda u: 0 if "_32_" in u[1] else 1 if "_16_" in u[1] else 2)  # longest first
 
     # kernel experiments: PRS_BUILD_ONLY="float_1,prs_b200" recompiles just those units and relinks with the

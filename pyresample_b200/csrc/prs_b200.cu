@@ -230,32 +230,51 @@ struct TargetTables {
 }  // namespace
 
 namespace prs {
-// launch_query_k<T, K, TK> is instantiated in the prs_query_inst.cu translation units, never here
-#define PRS_EXTERN_TK(T, K, TK) \
-    extern template int launch_query_k<T, K, TK>(const QueryParams &, const IndexView<T> &, cudaStream_t);
-#define PRS_EXTERN_INST(T, K) \
-    PRS_EXTERN_TK(T, K, PRS_TK_LONLAT) PRS_EXTERN_TK(T, K, PRS_TK_AREA_SEP) PRS_EXTERN_TK(T, K, PRS_TK_AREA_GEN)
-PRS_EXTERN_INST(float, 1)
-PRS_EXTERN_INST(float, 4)
-PRS_EXTERN_INST(float, 8)
-PRS_EXTERN_INST(float, 16)
-PRS_EXTERN_INST(float, 32)
-PRS_EXTERN_INST(double, 1)
-PRS_EXTERN_INST(double, 4)
-PRS_EXTERN_INST(double, 8)
-PRS_EXTERN_INST(double, 16)
-PRS_EXTERN_INST(double, 32)
+// launch_search<T, K, EPI> / launch_classify<T> are instantiated in prs_query_inst.cu / prs_classify_inst.cu, never here
+#define PRS_EXTERN_SEARCH(T, K, EPI)                                                                                   \
+    extern template int launch_search<T, K, EPI>(const QueryParams &, const IndexView<T> &, int64_t, const uint32_t *, \
+                                                 const uint32_t *, cudaStream_t);
+#define PRS_EXTERN_T(T)                                                                                              \
+    extern template int launch_classify<T>(const QueryParams &, const IndexView<T> &, int64_t, uint32_t *, uint32_t *, \
+                                           cudaStream_t);                                                            \
+    extern template int launch_coverage_t<T>(const QueryParams &, int, uint8_t *, cudaStream_t);                     \
+    PRS_EXTERN_SEARCH(T, 1, PRS_EPI_INFO)                                                                            \
+    PRS_EXTERN_SEARCH(T, 4, PRS_EPI_INFO)                                                                            \
+    PRS_EXTERN_SEARCH(T, 8, PRS_EPI_INFO)                                                                            \
+    PRS_EXTERN_SEARCH(T, 16, PRS_EPI_INFO)                                                                           \
+    PRS_EXTERN_SEARCH(T, 32, PRS_EPI_INFO)                                                                           \
+    PRS_EXTERN_SEARCH(T, 1, PRS_EPI_NEAREST)                                                                         \
+    PRS_EXTERN_SEARCH(T, 4, PRS_EPI_GAUSS)                                                                           \
+    PRS_EXTERN_SEARCH(T, 8, PRS_EPI_GAUSS)                                                                           \
+    PRS_EXTERN_SEARCH(T, 16, PRS_EPI_GAUSS)                                                                          \
+    PRS_EXTERN_SEARCH(T, 32, PRS_EPI_GAUSS)
+PRS_EXTERN_T(float)
+PRS_EXTERN_T(double)
 
-template <typename T, int K> int launch_query_tk(const QueryParams &P, const IndexView<T> &ix, int tk, cudaStream_t st)
+// Dispatch on (K, epilogue).  The top-k list width K is the smallest instantiated one >= k.
+template <typename T>
+int launch_search_k(const QueryParams &P, const IndexView<T> &ix, int64_t tiles, const uint32_t *live,
+                    const uint32_t *n_live, cudaStream_t st)
 {
-    switch (tk) {
-    case PRS_TK_LONLAT:
-        return launch_query_k<T, K, PRS_TK_LONLAT>(P, ix, st);
-    case PRS_TK_AREA_SEP:
-        return launch_query_k<T, K, PRS_TK_AREA_SEP>(P, ix, st);
+    const int k = P.k;
+    if (k > 32) return fail(PRS_ENOSUP, "neighbours > 32 is not supported");
+#define PRS_GO(K, EPI) return launch_search<T, K, EPI>(P, ix, tiles, live, n_live, st)
+    switch (P.mode) {
+    case PRS_EPI_NEAREST:
+        PRS_GO(1, PRS_EPI_NEAREST);
+    case PRS_EPI_GAUSS:
+        if (k <= 4) PRS_GO(4, PRS_EPI_GAUSS);
+        if (k <= 8) PRS_GO(8, PRS_EPI_GAUSS);
+        if (k <= 16) PRS_GO(16, PRS_EPI_GAUSS);
+        PRS_GO(32, PRS_EPI_GAUSS);
     default:
-        return launch_query_k<T, K, PRS_TK_AREA_GEN>(P, ix, st);
+        if (k <= 1) PRS_GO(1, PRS_EPI_INFO);
+        if (k <= 4) PRS_GO(4, PRS_EPI_INFO);
+        if (k <= 8) PRS_GO(8, PRS_EPI_INFO);
+        if (k <= 16) PRS_GO(16, PRS_EPI_INFO);
+        PRS_GO(32, PRS_EPI_INFO);
     }
+#undef PRS_GO
 }
 }  // namespace prs
 
@@ -300,6 +319,7 @@ template <typename T> int setup_target(QueryParams &P, const prs_target *tg, int
         P.tlon = tg->lon;
         P.tlat = tg->lat;
     }
+    P.tk = tk;
     return PRS_OK;
 }
 
@@ -314,6 +334,9 @@ int free_tables(TargetTables &tabs, cudaStream_t st)
     }
     return PRS_OK;
 }
+
+// Bytes of the live-tile list at the head of a staged call's scratch buffer (the target coordinates follow it).
+inline size_t live_list_bytes(int64_t tiles) { return ((size_t)(tiles + 1) * sizeof(uint32_t) + 255) & ~(size_t)255; }
 
 template <typename T> int launch_query_t(QueryParams &P, const prs_index *index, const prs_target *tg, cudaStream_t st)
 {
@@ -332,19 +355,24 @@ template <typename T> int launch_query_t(QueryParams &P, const prs_index *index,
     TargetTables tabs;
     int rc = setup_target<T>(P, tg, tk, tabs, st);
     if (rc != PRS_OK) return rc;
-    int k = P.k;
-    if (k <= 1)
-        rc = launch_query_tk<T, 1>(P, ix, tk, st);
-    else if (k <= 4)
-        rc = launch_query_tk<T, 4>(P, ix, tk, st);
-    else if (k <= 8)
-        rc = launch_query_tk<T, 8>(P, ix, tk, st);
-    else if (k <= 16)
-        rc = launch_query_tk<T, 16>(P, ix, tk, st);
-    else if (k <= 32)
-        rc = launch_query_tk<T, 32>(P, ix, tk, st);
-    else
+    if (P.k > 32) {
+        free_tables(tabs, st);
         return fail(PRS_ENOSUP, "neighbours > 32 is not supported");
+    }
+    if (P.n_t <= 0) return free_tables(tabs, st);
+    const int64_t tiles = tile_count(P);
+    if (tiles > 0x7FFFFFF0LL) return fail(PRS_ENOSUP, "target too large for one launch");
+    // work buffers: [0] = number of live tiles, [1..] = their ids; for targets whose coordinates are expensive
+    // (per-pixel inverse projection, explicit lon/lat) the (x, y, z, valid) hand-over from classification to search
+    const size_t xyz_bytes = tk == PRS_TK_AREA_SEP ? 0 : 4 * sizeof(T) * (size_t)P.n_t;
+    unsigned char *buf = (unsigned char *)P.scratch;
+    if (P.stage == 0) PRS_CK(cudaMallocAsync((void **)&buf, live_list_bytes(tiles) + xyz_bytes, st));
+    if (!buf) return fail(PRS_EINVAL, "staged call without scratch");
+    uint32_t *n_live = (uint32_t *)buf, *live = n_live + 1;
+    if (xyz_bytes) P.target_xyz = buf + live_list_bytes(tiles);
+    if (P.stage != 2) rc = launch_classify<T>(P, ix, tiles, live, n_live, st);
+    if (rc == PRS_OK && P.stage != 1) rc = launch_search_k<T>(P, ix, tiles, live, n_live, st);
+    if (P.stage == 0) PRS_CK(cudaFreeAsync(buf, st));
     int rc2 = free_tables(tabs, st);
     return rc != PRS_OK ? rc : rc2;
 }
@@ -597,7 +625,10 @@ int64_t prs_resample_scratch_bytes(const prs_target *target)
 {
     if (!target || target->kind != PRS_TARGET_AREA) return 0;
     const int64_t tiles = ((target->grid.width + 31) / 32) * ((target->nrows + PRS_TILE_ROWS - 1) / PRS_TILE_ROWS);
-    return (int64_t)sizeof(uint32_t) * (tiles + 1);
+    const bool separable = target->proj.kind == PRS_PROJ_LONGLAT || target->proj.kind == PRS_PROJ_EQC ||
+                           target->proj.kind == PRS_PROJ_MERC;
+    const size_t coord = target->dtype == PRS_F64 ? sizeof(double) : sizeof(float);
+    return (int64_t)(live_list_bytes(tiles) + (separable ? 0 : 4 * coord * (size_t)target->n));
 }
 
 static int resample_nearest_stage(int stage, const prs_index *index, const prs_target *target, double radius,

@@ -1,50 +1,62 @@
-// Host-side launch of the query kernels for one (tree dtype, K, target kind).  launch_query_k is instantiated
-// explicitly in prs_query_inst.cu - one translation unit per (T, K), and per target kind for the wide top-k lists,
-// whose unrolled insertion networks take minutes to compile - so that the units build in parallel.
+// Host-side launch of the classification and search kernels.  The templates are instantiated explicitly in
+// prs_classify_inst.cu (tree dtype) and prs_query_inst.cu (tree dtype, K, epilogue) - one translation unit each, so
+// that the wide top-k lists, whose unrolled insertion networks take minutes to compile, build in parallel.
 #pragma once
 #include "prs_query.cuh"
 
 namespace prs {
 
-template <typename T, int K, int TK> int launch_query_k(const QueryParams &P, const IndexView<T> &ix, cudaStream_t st)
+inline int64_t tile_count(const QueryParams &P)
 {
-    if (P.n_t <= 0) return PRS_OK;
-    int64_t tiles;
-    if (TK == PRS_TK_LONLAT)
-        tiles = (P.n_t + 32 * QROWS - 1) / (32 * QROWS);
-    else
-        tiles = (int64_t)P.tiles_x * ((P.nrows + QROWS - 1) / QROWS);
-    if (tiles > 0x7FFFFFF0LL) return fail(PRS_ENOSUP, "target too large for one launch");
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        PRS_CK(cudaGetDevice(&dev));
-        PRS_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    if (P.tk == PRS_TK_LONLAT) return (P.n_t + 32 * QROWS - 1) / (32 * QROWS);
+    return (int64_t)P.tiles_x * ((P.nrows + QROWS - 1) / QROWS);
+}
+
+// Classification + fill of the dead tiles (classify_kernel); live[] / n_live receive the tiles left to search.
+template <typename T, int TK>
+int launch_classify_tk(const QueryParams &P, const IndexView<T> &ix, int64_t tiles, uint32_t *live, uint32_t *n_live,
+                       cudaStream_t st)
+{
+    PRS_CK(cudaMemsetAsync(n_live, 0, sizeof(uint32_t), st));
+    classify_kernel<T, TK><<<(unsigned)((tiles + QWARPS - 1) / QWARPS), QWARPS * 32, 0, st>>>(P, ix, (uint32_t)tiles, live, n_live);
+    PRS_CKL();
+    return PRS_OK;
+}
+template <typename T>
+int launch_classify(const QueryParams &P, const IndexView<T> &ix, int64_t tiles, uint32_t *live, uint32_t *n_live,
+                    cudaStream_t st)
+{
+    switch (P.tk) {
+    case PRS_TK_LONLAT:
+        return launch_classify_tk<T, PRS_TK_LONLAT>(P, ix, tiles, live, n_live, st);
+    case PRS_TK_AREA_SEP:
+        return launch_classify_tk<T, PRS_TK_AREA_SEP>(P, ix, tiles, live, n_live, st);
+    default:
+        return launch_classify_tk<T, PRS_TK_AREA_GEN>(P, ix, tiles, live, n_live, st);
     }
-    uint32_t *buf = P.scratch;  // [0] = number of live tiles, [1..] = their ids
-    if (P.stage == 0) PRS_CK(cudaMallocAsync((void **)&buf, sizeof(uint32_t) * (size_t)(tiles + 1), st));
-    if (!buf) return fail(PRS_EINVAL, "staged call without scratch");
-    uint32_t *n_live = buf, *live = buf + 1;
-    QueryParams Q = P;  // + the coordinate hand-over buffer where the target transform is expensive
-    void *xyz = nullptr;
-    if (TK != PRS_TK_AREA_SEP && P.stage == 0) {
-        PRS_CK(cudaMallocAsync(&xyz, 4 * sizeof(T) * (size_t)P.n_t, st));
-        Q.target_xyz = xyz;
+}
+
+// Search of the live tiles (query_kernel): persistent-style grid, a multiple of the SM count, blocks stride over
+// the live list.  Dynamic shared memory: the record staging buffer (+ the row stage of the nearest epilogue).
+template <typename T, int K, int EPI>
+int launch_search(const QueryParams &P, const IndexView<T> &ix, int64_t tiles, const uint32_t *live,
+                  const uint32_t *n_live, cudaStream_t st)
+{
+    int dev = 0;
+    PRS_CK(cudaGetDevice(&dev));
+    static int n_sm[64] = {0};
+    static bool configured[64] = {false};
+    const int slot = dev < 0 || dev >= 64 ? 0 : dev;
+    const size_t smem = PRS_STAGE_BYTES(K) + (EPI == PRS_EPI_NEAREST ? QROWS * 32 * STAGE_ROW_BYTES : 0);
+    if (!configured[slot] || slot != dev) {
+        PRS_CK(cudaDeviceGetAttribute(&n_sm[slot], cudaDevAttrMultiProcessorCount, dev));
+        PRS_CK(cudaFuncSetAttribute(query_kernel<T, K, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[slot] = true;
     }
-    if (P.stage != 2) {
-        PRS_CK(cudaMemsetAsync(n_live, 0, sizeof(uint32_t), st));
-        classify_kernel<T, K, TK><<<(unsigned)((tiles + QWARPS - 1) / QWARPS), QWARPS * 32, 0, st>>>(Q, ix, (uint32_t)tiles, live, n_live);
-        PRS_CKL();
-    }
-    if (P.stage != 1) {
-        // search: persistent-style grid, a multiple of the SM count, blocks stride over the live list
-        int64_t qgrid = (int64_t)n_sm * 32;
-        if (qgrid > tiles) qgrid = tiles;
-        query_kernel<T, K, TK><<<(unsigned)qgrid, QROWS * 32, 0, st>>>(Q, ix, live, n_live);
-        PRS_CKL();
-    }
-    if (xyz) PRS_CK(cudaFreeAsync(xyz, st));
-    if (P.stage == 0) PRS_CK(cudaFreeAsync(buf, st));
+    int64_t qgrid = (int64_t)n_sm[slot] * 32;
+    if (qgrid > tiles) qgrid = tiles;
+    query_kernel<T, K, EPI><<<(unsigned)qgrid, QROWS * 32, smem, st>>>(P, ix, live, n_live);
+    PRS_CKL();
     return PRS_OK;
 }
 

@@ -240,7 +240,7 @@ __device__ inline bool inv_merc(const prs_proj_params &P, double x, double y, do
 
 // Projected (x, y) in the CRS's own units -> geodetic lon/lat in degrees (double).
 // Off-projection points give +inf for both, like pyproj with errcheck=False.
-__device__ inline void proj_inverse(const prs_proj_params &P, double x, double y, double &lon, double &lat)
+static __device__ __noinline__ void proj_inverse(const prs_proj_params &P, double x, double y, double &lon, double &lat)
 {
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     if (P.kind == PRS_PROJ_LONGLAT) {

@@ -5,9 +5,11 @@
 //   A. classify_kernel, one warp per tile: bound the tile's points by a spherical cap and ask the L2-resident
 //      coarse table whether ANY source point lies within (tile cap + radius).  Wide target grids are mostly far
 //      from the swath: such tiles get their final result (fill / sentinels) streamed out right away;
-//   B. query_kernel, one thread per point of the remaining tiles: grow a block of cells around the point's own
-//      cell until k candidates are found, then visit exactly the cells that can still beat the k-th distance;
-//   4. epilogue: neighbour info, or the gathered / weighted samples (nearest rows go through shared memory
+//   B. query_kernel, one block per remaining tile, one thread per point: the block stages the candidate records of
+//      the tile in shared memory with bulk copies (cp.async.bulk + mbarrier), every thread scans the 3x3 block of
+//      cells around its own point from there, then proves the result or visits exactly the cells that can still
+//      beat the k-th distance (general search, global memory);
+//   C. epilogue: neighbour info, or the gathered / weighted samples (nearest rows go through shared memory
 //      so that the warp writes contiguous 128-byte segments).
 #pragma once
 #include "prs_common.cuh"
@@ -350,82 +352,203 @@ __device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T 
     return top;
 }
 
-// Exact bounded k-NN of one query point.  dub = (T)(radius^2); candidates need d2 < dub.
-// Hot path: scan the 3x3 block of cells around the point's own cell - three contiguous record runs, walked as ONE
-// flattened loop so that the lanes of a warp stay busy - then prove with the closed-form cap bounds that nothing
-// outside the block can beat or tie the k-th candidate.  Anything else goes to knn_search_general.
-template <typename T, int K>
-__device__ __forceinline__ void knn_search(const IndexView<T> &ix, T qx, T qy, T qz, T dub, float s2r, float sr,
-                                           TopK<T, K> &top)
+// ------------------------------------------------------------------------------------------ bulk-copy staging
+// Blackwell / Hopper asynchronous-copy primitives used by the search kernel: 1-D bulk copies global -> shared
+// (cp.async.bulk, SASS UBLKCP) whose completion is counted in bytes on a shared-memory mbarrier.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// dst (shared) and src (global) 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// orders this thread's earlier generic-proxy accesses of shared memory before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Candidate records of one tile, staged in shared memory.  The threads of a tile (32 x QROWS neighbouring target
+// points) scan almost the same cells, and one row of cells is ONE contiguous run of records: the block takes, for
+// every row of cells any of its points touches, the span of cells between the leftmost and the rightmost touched
+// one (the "hull" of the tile's 3x3 blocks - tight also when the tile lies diagonally on the cube face) and fetches
+// each row's run with one bulk copy.
+constexpr int HULL_ROWS = 64;  // rows of cells a staged tile may span (rows are slotted modulo this)
+// Shared memory for staged records per block: a tile's hull holds roughly (points per cell) x (cells the tile
+// covers + a margin of one cell), and cells are sized for ~max(2, k / 2) points - narrow lists need less.
+#ifndef PRS_STAGE_BYTES
+#define PRS_STAGE_BYTES(K) ((K) <= 1 ? 16384 : (K) <= 4 ? 32768 : 49152)
+#endif
+struct StageCtx {
+    unsigned long long bar;          // mbarrier: 32 arrivals (warp 0) + the bytes of the row copies
+    int umin[HULL_ROWS], umax[HULL_ROWS];
+    uint32_t gstart[HULL_ROWS];      // index of the first staged record of the row in recs[]
+    uint32_t sbase[HULL_ROWS];       // ... and its slot in the staging buffer
+    int vlo, vhi;
+    unsigned faces;
+    int staged;                      // 1: the tile's candidates are (being) staged
+};
+
+// Home cell of a query point and the (clipped) 3x3 block around it.
+struct Home {
+    int face, cu, cv;
+    CellRect hb;  // empty (u0 > u1) when the block lies outside the table
+};
+template <typename T> __device__ __forceinline__ Home home_of(const IndexView<T> &ix, T qx, T qy, T qz)
 {
     const float invR = (float)(1.0 / PRS_R);
     const float fx = (float)qx * invR, fy = (float)qy * invR, fz = (float)qz * invR;
-    const int G = ix.G;
-    int hface;
+    Home h;
     float hu, hv;
-    face_uv(fx, fy, fz, hface, hu, hv);
-    const int cu = cell_coord(warp_uv(hu), G), cv = cell_coord(warp_uv(hv), G);
+    face_uv(fx, fy, fz, h.face, hu, hv);
+    h.cu = cell_coord(warp_uv(hu), ix.G);
+    h.cv = cell_coord(warp_uv(hv), ix.G);
     const FaceTable &ft = ix.fine;
-    CellRect hb;
-    hb.u0 = max(cu - 1, ft.fu0[hface]);
-    hb.u1 = min(cu + 1, ft.fu0[hface] + ft.fw[hface] - 1);
-    hb.v0 = max(cv - 1, ft.fv0[hface]);
-    hb.v1 = min(cv + 1, ft.fv0[hface] + ft.fh[hface] - 1);
-    if (hb.u0 <= hb.u1 && hb.v0 <= hb.v1) {
-        const int fw = ft.fw[hface];
-        const uint32_t *row = ix.cell_start + ft.base[hface] + (int64_t)(hb.v0 - ft.fv0[hface]) * fw - ft.fu0[hface];
-        const int nrows = hb.v1 - hb.v0 + 1;
-        // all run bounds first (independent loads in flight together), then one flattened candidate loop
-        uint32_t s0 = __ldg(row + hb.u0), e0 = __ldg(row + hb.u1 + 1);
-        uint32_t s1 = 0, e1 = 0, s2 = 0, e2 = 0;
-        if (nrows > 1) {
-            s1 = __ldg(row + fw + hb.u0);
-            e1 = __ldg(row + fw + hb.u1 + 1);
-        }
-        if (nrows > 2) {
-            s2 = __ldg(row + 2 * fw + hb.u0);
-            e2 = __ldg(row + 2 * fw + hb.u1 + 1);
-        }
-        // walk the point's own row of cells first: its candidates are the likeliest neighbours, so the k-th
-        // distance tightens early and fewer of the later candidates have to be inserted into the list
-        if (K > 1 && nrows > 1 && cv != hb.v0) {
-            const uint32_t ts = s0, te = e0;
-            s0 = s1, e0 = e1;
-            s1 = ts, e1 = te;
-        }
-        const uint32_t n0 = e0 - s0, n01 = n0 + (e1 - s1), total = n01 + (e2 - s2);
-        // records are fetched PRS_SCAN_BATCH at a time before any is examined: the loads of a batch are in flight
-        // together (one load per iteration left the thread waiting a full memory round trip per candidate)
-        constexpr int B = PRS_SCAN_BATCH(K);
-#pragma unroll 1
-        for (uint32_t t0 = 0; t0 < total; t0 += B) {
-            Rec<T> r[B];
-#pragma unroll
-            for (int u = 0; u < B; ++u) {
-                const uint32_t t = min(t0 + u, total - 1);
-                const uint32_t i = t < n0 ? s0 + t : (t < n01 ? s1 + (t - n0) : s2 + (t - n01));
-                r[u] = load_rec(ix.recs + i);
-            }
-#pragma unroll
-            for (int u = 0; u < B; ++u)
-                if (t0 + u < total)
-                    top.template offer<false>(dist2<T>(qx, qy, qz, r[u].x, r[u].y, r[u].z), r[u].idx, dub);
-        }
-    } else {
-        hb.u0 = hb.v0 = 1;  // home block outside the table: nothing visited
-        hb.u1 = hb.v1 = 0;
+    h.hb.u0 = max(h.cu - 1, ft.fu0[h.face]);
+    h.hb.u1 = min(h.cu + 1, ft.fu0[h.face] + ft.fw[h.face] - 1);
+    h.hb.v0 = max(h.cv - 1, ft.fv0[h.face]);
+    h.hb.v1 = min(h.cv + 1, ft.fv0[h.face] + ft.fh[h.face] - 1);
+    if (ft.fw[h.face] == 0 || h.hb.u0 > h.hb.u1 || h.hb.v0 > h.hb.v1) {
+        h.hb.u0 = h.hb.v0 = 1;
+        h.hb.u1 = h.hb.v1 = 0;
     }
+    return h;
+}
+
+// Bounds [s, e) in recs[] of the (up to three) rows of the home block, the point's own row first: its candidates
+// are the likeliest neighbours, so the k-th distance tightens early and fewer later candidates enter the list.
+struct HomeRuns {
+    uint32_t s[3], e[3];  // empty run (s == e) for a row outside the table
+    int v[3];
+};
+template <typename T> __device__ __forceinline__ HomeRuns home_runs(const IndexView<T> &ix, const Home &h)
+{
+    HomeRuns r;
+    r.v[0] = h.cv, r.v[1] = h.cv - 1, r.v[2] = h.cv + 1;
+    const FaceTable &ft = ix.fine;
+    const int fw = ft.fw[h.face];
+    const uint32_t *row0 = ix.cell_start + ft.base[h.face] - (int64_t)ft.fv0[h.face] * fw - ft.fu0[h.face];
+    // all run bounds first: six independent loads in flight together
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        r.s[j] = r.e[j] = 0;
+        if (h.hb.u0 <= h.hb.u1 && r.v[j] >= h.hb.v0 && r.v[j] <= h.hb.v1) {
+            const uint32_t *row = row0 + (int64_t)r.v[j] * fw;
+            r.s[j] = __ldg(row + h.hb.u0);
+            r.e[j] = __ldg(row + h.hb.u1 + 1);
+        }
+    }
+    return r;
+}
+
+// Hot path, records from global memory: the runs are walked as ONE flattened loop so that the lanes of a warp stay
+// busy; records are fetched PRS_SCAN_BATCH at a time before any is examined (one load per iteration left the
+// thread waiting a full memory round trip per candidate).
+template <typename T, int K>
+__device__ __forceinline__ void scan_home_global(const IndexView<T> &ix, const HomeRuns &hr, T qx, T qy, T qz, T dub,
+                                                 TopK<T, K> &top)
+{
+    const uint32_t n0 = hr.e[0] - hr.s[0], n01 = n0 + (hr.e[1] - hr.s[1]), total = n01 + (hr.e[2] - hr.s[2]);
+    constexpr int B = PRS_SCAN_BATCH(K);
+#pragma unroll 1
+    for (uint32_t t0 = 0; t0 < total; t0 += B) {
+        Rec<T> r[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const uint32_t t = min(t0 + u, total - 1);
+            const uint32_t i = t < n0 ? hr.s[0] + t : (t < n01 ? hr.s[1] + (t - n0) : hr.s[2] + (t - n01));
+            r[u] = load_rec(ix.recs + i);
+        }
+#pragma unroll
+        for (int u = 0; u < B; ++u)
+            if (t0 + u < total)
+                top.template offer<false>(dist2<T>(qx, qy, qz, r[u].x, r[u].y, r[u].z), r[u].idx, dub);
+    }
+}
+
+__device__ __forceinline__ Rec<float> lds_rec(const Rec<float> *p)
+{
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    Rec<float> r;
+    r.x = v.x, r.y = v.y, r.z = v.z, r.idx = __float_as_uint(v.w);
+    return r;
+}
+__device__ __forceinline__ Rec<double> lds_rec(const Rec<double> *p)
+{
+    const double2 a = reinterpret_cast<const double2 *>(p)[0], b = reinterpret_cast<const double2 *>(p)[1];
+    Rec<double> r;
+    r.x = a.x, r.y = a.y, r.z = b.x, r.idx = (uint32_t)(__double_as_longlong(b.y) & 0xFFFFFFFFLL), r.pad = 0;
+    return r;
+}
+
+// Hot path, records staged in shared memory (same order of candidates as scan_home_global).
+template <typename T, int K>
+__device__ __forceinline__ void scan_home_staged(const StageCtx &sc, const Rec<T> *srecs, const HomeRuns &hr, T qx, T qy,
+                                                 T qz, T dub, TopK<T, K> &top)
+{
+    // slot of the first record of each run in the staging buffer
+    uint32_t b[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int slot = hr.v[j] & (HULL_ROWS - 1);
+        b[j] = sc.sbase[slot] + (hr.s[j] - sc.gstart[slot]);
+    }
+    const uint32_t n0 = hr.e[0] - hr.s[0], n01 = n0 + (hr.e[1] - hr.s[1]), total = n01 + (hr.e[2] - hr.s[2]);
+#pragma unroll 1
+    for (uint32_t t = 0; t < total; ++t) {
+        const uint32_t i = t < n0 ? b[0] + t : (t < n01 ? b[1] + (t - n0) : b[2] + (t - n01));
+        const Rec<T> r = lds_rec(srecs + i);
+        top.template offer<false>(dist2<T>(qx, qy, qz, r.x, r.y, r.z), r.idx, dub);
+    }
+}
+
+// After the home block: done when the cap of the k-th distance provably stays inside the block (closed-form bounds,
+// home face only); anything else continues in knn_search_general.
+template <typename T, int K>
+__device__ __forceinline__ void knn_finish(const IndexView<T> &ix, const Home &h, T qx, T qy, T qz, T dub, float s2r,
+                                           float sr, TopK<T, K> &top)
+{
+    const float invR = (float)(1.0 / PRS_R);
+    const float fx = (float)qx * invR, fy = (float)qy * invR, fz = (float)qz * invR;
     if (top.full()) {
         const float s2b = cap_s2<T>(top.d[K - 1]);
         float b[4];
-        face_bounds(hface, fx, fy, fz, s2b, sqrtf(s2b), b);
+        face_bounds(h.face, fx, fy, fz, s2b, sqrtf(s2b), b);
         if (bounds_inside_face(b)) {
-            CellRect c = bounds_to_cells(b, G);
+            CellRect c = bounds_to_cells(b, ix.G);
             // cells of the bound cap outside the table hold no points; inside the visited block nothing is left
-            if (!clip_rect(ft, hface, c) || (c.u0 >= hb.u0 && c.u1 <= hb.u1 && c.v0 >= hb.v0 && c.v1 <= hb.v1)) return;
+            if (!clip_rect(ix.fine, h.face, c) ||
+                (c.u0 >= h.hb.u0 && c.u1 <= h.hb.u1 && c.v0 >= h.hb.v0 && c.v1 <= h.hb.v1))
+                return;
         }
     }
-    top = knn_search_general<T, K>(ix, qx, qy, qz, dub, s2r, sr, top, hb, hface, cu, cv);
+    top = knn_search_general<T, K>(ix, qx, qy, qz, dub, s2r, sr, top, h.hb, h.face, h.cu, h.cv);
 }
 
 // ------------------------------------------------------------------------------------------ targets
@@ -455,6 +578,7 @@ struct QueryParams {
     int64_t row_block, row_stride;  // block-cyclic row ownership (row_block == 0: contiguous)
     int nrows;      // area targets: local rows of this call
     int tiles_x;    // tiles per tile-row
+    int tk;         // PRS_TK_* (a template parameter of the classification, a run-time value for the search)
     const void *col_tab, *row_tab;
     const uint8_t *col_ok, *row_ok;
     // search
@@ -480,13 +604,14 @@ struct QueryParams {
     int uniform_sigma;
     double fill;
     void *stddev_out, *count_out;
+    // Targets whose coordinates are expensive (per-pixel inverse projection, explicit lon/lat): classification
+    // computes every point anyway and leaves (x, y, z, valid) here for the search (4 values of the tree dtype).
+    // Always set for PRS_TK_LONLAT / PRS_TK_AREA_GEN; separable areas use the tables instead.
+    void *target_xyz;
     // staged execution (prs_resample_nearest_fill / _search): 0 = classify + fill + search in one call,
     // 1 = classify + fill only (live tiles listed in scratch), 2 = search the tiles listed in scratch
-    // targets whose coordinates are expensive (per-pixel inverse projection, explicit lon/lat): classification
-    // computes every point anyway and leaves (x, y, z, valid) here for the search (4 values of the tree dtype)
-    void *target_xyz;
     int stage;
-    uint32_t *scratch;       // caller-owned: [0] = number of live tiles, [1..] = their ids
+    uint32_t *scratch;       // caller-owned: [0] = number of live tiles, [1..] = their ids, then the coordinates
     uint8_t *tile_row_live;  // stage 1: [tile row] = 1 when the tile row holds a live tile
 };
 
@@ -538,32 +663,20 @@ __device__ __forceinline__ void load_channels(const Td *__restrict__ p, int nc, 
     }
 }
 
-// _resample_with_weights (kd_tree.py:741-818) + _calculate_uncertainty (kd_tree.py:821-859) for one target point,
-// fused behind the search.  T: distance dtype (the Gaussian is evaluated in it, kd_tree.py:165), Td: data dtype,
-// Ta: accumulation / output dtype (numpy promotion: float64 for multi-channel data, kd_tree.py:783).
-// Channels are processed four at a time so that a neighbour's row is read with 16-byte loads; per channel the
-// neighbours are accumulated in order i = 0..k-1 exactly like the reference's Python loop.
+// _resample_with_weights (kd_tree.py:741-818) + _calculate_uncertainty (kd_tree.py:821-859) for one target point that
+// has at least one neighbour, fused behind the search.  T: distance dtype (the Gaussian is evaluated in it,
+// kd_tree.py:165), Td: data dtype, Ta: accumulation / output dtype (numpy promotion: float64 for multi-channel data,
+// kd_tree.py:783).  Channels are processed four at a time so that a neighbour's row is read with 16-byte loads; per
+// channel the neighbours are accumulated in order i = 0..k-1 exactly like the reference's Python loop.
 template <typename T, typename Ta, typename Td, int K>
 __device__ __noinline__ void gauss_epilogue(const QueryParams &P, const IndexView<T> &ix, int64_t p,
-                                            const TopK<T, K> &top, bool valid)
+                                            const TopK<T, K> &top)
 {
     const int C = P.channels, k = P.k;
     const bool want_uncert = P.stddev_out != nullptr;
     Ta *out = (Ta *)P.out + (size_t)p * C;
     Ta *sd_out = want_uncert ? (Ta *)P.stddev_out + (size_t)p * C : nullptr;
     Ta *cnt_out = want_uncert ? (Ta *)P.count_out + (size_t)p * C : nullptr;
-    if (!valid || top.id[0] == PRS_NONE) {
-        // not in valid_output_index (kd_tree.py:719-723, 865-868), or no neighbour at all: every weight is zero, so
-        // norm == 0 and the pixel is the fill value whatever new_data[0] holds (kd_tree.py:807-809)
-        for (int c = 0; c < C; ++c) {
-            out[c] = (Ta)P.fill;
-            if (want_uncert) {
-                sd_out[c] = Ar<Ta>::nan();
-                cnt_out[c] = 0;
-            }
-        }
-        return;
-    }
     const Td *data = (const Td *)P.data;
     const bool vec_ok = (C & 3) == 0 && ((reinterpret_cast<uintptr_t>(data) & 15) == 0);
     T dist2w[K];  // r ** 2 with r the rounded distance; missing neighbours: distance 1 (kd_tree.py:767-768)
@@ -581,6 +694,7 @@ __device__ __noinline__ void gauss_epilogue(const QueryParams &P, const IndexVie
 #pragma unroll
         for (int i = 0; i < K; ++i) wu[i] = (Ta)Ar<T>::exp(Ar<T>::div(-dist2w[i], s2));
     }
+#pragma unroll 1
     for (int c0 = 0; c0 < C; c0 += 4) {
         const int nc = min(4, C - c0);
         Ta res[4] = {0, 0, 0, 0}, norm[4] = {0, 0, 0, 0};
@@ -646,6 +760,22 @@ __device__ __noinline__ void gauss_epilogue(const QueryParams &P, const IndexVie
     }
 }
 
+// A weighted pixel without any neighbour (or outside valid_output_index, kd_tree.py:719-723, 865-868): every weight is
+// zero, so norm == 0 and the pixel is the fill value whatever new_data[0] holds (kd_tree.py:807-809).
+template <typename Ta> __device__ __forceinline__ void gauss_empty(const QueryParams &P, int64_t p)
+{
+    const int C = P.channels;
+    Ta *out = (Ta *)P.out + (size_t)p * C;
+    for (int c = 0; c < C; ++c) out[c] = (Ta)P.fill;
+    if (P.stddev_out) {
+        Ta *sd = (Ta *)P.stddev_out + (size_t)p * C, *cnt = (Ta *)P.count_out + (size_t)p * C;
+        for (int c = 0; c < C; ++c) {
+            sd[c] = Ar<Ta>::nan();
+            cnt[c] = 0;
+        }
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll
@@ -656,6 +786,12 @@ __device__ __forceinline__ float warp_max(float v)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 
@@ -691,6 +827,14 @@ __device__ __forceinline__ int64_t global_row(int64_t row0, int64_t row_block, i
     return row0 + s * row_stride + (l - s * row_block);
 }
 
+// lon/lat of one pixel of a general (non-separable) area: ONE out-of-line copy of the projection code per kernel
+// (inlined at every use the double-precision inverse projections made the kernels hundreds of KB of SASS).
+template <typename T>
+__device__ __noinline__ void area_point_lonlat(const QueryParams &P, int trow, int tcol, T &lon, T &lat)
+{
+    area_pixel_lonlat<T>(P.proj, P.grid, global_row(P.row0, P.row_block, P.row_stride, trow), tcol, lon, lat);
+}
+
 // Target coordinates of one point (kd_tree.py:513-534): validity + ECEF in the tree dtype.
 template <typename T, int TK>
 __device__ __forceinline__ bool target_point(const QueryParams &P, int64_t p, int trow, int tcol, T &qx, T &qy, T &qz)
@@ -710,96 +854,13 @@ __device__ __forceinline__ bool target_point(const QueryParams &P, int64_t p, in
             lon = ((const T *)P.tlon)[p];
             lat = ((const T *)P.tlat)[p];
         } else {
-            area_pixel_lonlat<T>(P.proj, P.grid, global_row(P.row0, P.row_block, P.row_stride, trow), tcol, lon, lat);
+            area_point_lonlat<T>(P, trow, tcol, lon, lat);
         }
         valid = lonlat_in_range<T>(lon, lat);
         if (valid) lonlat_to_xyz(lon, lat, qx, qy, qz);
     }
     if (P.valid_extra) valid = valid && P.valid_extra[p];
     return valid;
-}
-
-// Result of one target point (p < 0: lane has no point).  All 32 lanes of the warp call this together: nearest rows
-// are staged in shared memory and streamed out as contiguous 128-byte segments.
-template <typename T, int K, int TK>
-__device__ __forceinline__ void epilogue(const QueryParams &P, const IndexView<T> &ix, int64_t p, int trow, int tcol,
-                                         int lane, unsigned char *stage, const TopK<T, K> &top, bool valid)
-{
-    if (P.mode == PRS_EPI_INFO) {
-        bool kth = false;
-        if (p >= 0) {
-            const int k = P.k;
-            uint32_t *io = P.idx_out + (size_t)p * k;
-            T *dout = P.dist_out ? (T *)P.dist_out + (size_t)p * k : nullptr;
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-                if (i < k) {
-                    uint32_t s = top.id[i];
-                    io[i] = s == PRS_NONE ? ix.n_valid : (ix.rank ? __ldg(ix.rank + s) : s);
-                    if (dout) dout[i] = s == PRS_NONE ? Ar<T>::inf() : Ar<T>::sqrt(top.d[i]);
-                    if (i == k - 1 && s != PRS_NONE) kth = true;
-                }
-            }
-            if (P.valid_out) P.valid_out[p] = valid ? 1 : 0;
-        }
-        if (P.flags) {
-            if (kth && P.flags[0] == 0) P.flags[0] = 1;
-            unsigned bad = __ballot_sync(0xffffffffu, p >= 0 && !valid);
-            if (lane == 0 && bad) atomicAdd(&P.flags[1], (unsigned)__popc(bad));
-        }
-    } else if (P.mode == PRS_EPI_NEAREST) {
-        const void *src = top.id[0] == PRS_NONE ? P.fill_row
-                                                : (const void *)((const char *)P.data + (size_t)top.id[0] * P.row_bytes);
-        const bool staged = P.row_bytes <= STAGE_ROW_BYTES && TK != PRS_TK_LONLAT;
-        if (staged) {
-            const int rb = P.row_bytes;
-            if (p >= 0) copy_row(stage + lane * rb, src, rb, P.vec);
-            __syncwarp();
-            if (trow < P.nrows) {
-                const int W = (int)P.grid.width;
-                const int c0 = tcol - lane;
-                const int span = min(32, W - c0) * rb;
-                char *dst = (char *)P.out + ((size_t)trow * W + c0) * rb;
-                if ((rb & 3) == 0) {
-                    for (int o = lane * 4; o < span; o += 128)
-                        *reinterpret_cast<uint32_t *>(dst + o) = *reinterpret_cast<const uint32_t *>(stage + o);
-                } else {
-                    for (int o = lane; o < span; o += 32) dst[o] = stage[o];
-                }
-            }
-            __syncwarp();
-        } else if (p >= 0) {
-            copy_row((char *)P.out + (size_t)p * P.row_bytes, src, P.row_bytes, P.vec);
-        }
-    } else if (p >= 0) {
-        if (P.flags) {
-            bool kth = false;
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-                if (i == P.k - 1 && top.id[i] != PRS_NONE) kth = true;
-            if (kth && P.flags[0] == 0) P.flags[0] = 1;
-        }
-        if (P.acc_f64) {
-            if (P.data_f64)
-                gauss_epilogue<T, double, double, K>(P, ix, p, top, valid);
-            else
-                gauss_epilogue<T, double, float, K>(P, ix, p, top, valid);
-        } else {
-            gauss_epilogue<T, float, float, K>(P, ix, p, top, valid);
-        }
-    }
-}
-
-// Classification, one warp per tile: bound the tile's points by a spherical cap and ask the L2-resident coarse table
-// whether ANY source point lies within (cap + radius).  Tiles that see nothing ("dead") get their final result
-// without a search (fill value / "no neighbour" sentinels) - on wide target grids that is most of the output,
-// written as a stream; the other tiles are listed in live[] for the search kernel.
-// tile_live: can any point of the tile have a neighbour?  vmask = this lane's valid points (bit j = tile row j).
-__device__ __forceinline__ float warp_min(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
 }
 
 // Target coordinates handed from classification to the search: (x, y, z, valid != 0) per point.
@@ -825,6 +886,143 @@ template <typename T> __device__ __forceinline__ bool load_target_xyz(const void
     x = (T)a.x, y = (T)a.y, z = (T)b.x;
     return b.y != 0.0;
 }
+
+// The search's view of a target point: separable areas recompute it from the tables (two multiplies), everything
+// else reads what classification left in target_xyz.
+template <typename T>
+__device__ __forceinline__ bool query_point(const QueryParams &P, int64_t p, int trow, int tcol, T &qx, T &qy, T &qz)
+{
+    if (P.tk == PRS_TK_AREA_SEP) return target_point<T, PRS_TK_AREA_SEP>(P, p, trow, tcol, qx, qy, qz);
+    return load_target_xyz<T>(P.target_xyz, p, qx, qy, qz);
+}
+
+// ------------------------------------------------------------------------------------------ results
+// Neighbour info of one point (kd_tree.py:545-548): ranks, distances, valid_output_index.  All 32 lanes call this.
+template <typename T, int K>
+__device__ __forceinline__ void emit_info(const QueryParams &P, const IndexView<T> &ix, int64_t p, int lane,
+                                          const TopK<T, K> &top, bool valid)
+{
+    bool kth = false;
+    if (p >= 0) {
+        const int k = P.k;
+        uint32_t *io = P.idx_out + (size_t)p * k;
+        T *dout = P.dist_out ? (T *)P.dist_out + (size_t)p * k : nullptr;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            if (i < k) {
+                uint32_t s = top.id[i];
+                io[i] = s == PRS_NONE ? ix.n_valid : (ix.rank ? __ldg(ix.rank + s) : s);
+                if (dout) dout[i] = s == PRS_NONE ? Ar<T>::inf() : Ar<T>::sqrt(top.d[i]);
+                if (i == k - 1 && s != PRS_NONE) kth = true;
+            }
+        }
+        if (P.valid_out) P.valid_out[p] = valid ? 1 : 0;
+    }
+    if (P.flags) {
+        if (kth && P.flags[0] == 0) P.flags[0] = 1;
+        unsigned bad = __ballot_sync(0xffffffffu, p >= 0 && !valid);
+        if (lane == 0 && bad) atomicAdd(&P.flags[1], (unsigned)__popc(bad));
+    }
+}
+
+// Nearest-neighbour row of one point (kd_tree.py:705-711).  All 32 lanes call this: rows of up to STAGE_ROW_BYTES
+// are staged in shared memory and streamed out as contiguous 128-byte segments.  src_index == PRS_NONE: fill row.
+__device__ __forceinline__ void emit_nearest(const QueryParams &P, int64_t p, int trow, int tcol, int lane,
+                                             unsigned char *stage, uint32_t src_index)
+{
+    const void *src = src_index == PRS_NONE ? P.fill_row
+                                            : (const void *)((const char *)P.data + (size_t)src_index * P.row_bytes);
+    const bool staged = P.row_bytes <= STAGE_ROW_BYTES && P.tk != PRS_TK_LONLAT;
+    if (staged) {
+        const int rb = P.row_bytes;
+        if (p >= 0) copy_row(stage + lane * rb, src, rb, P.vec);
+        __syncwarp();
+        if (trow < P.nrows) {
+            const int W = (int)P.grid.width;
+            const int c0 = tcol - lane;
+            const int span = min(32, W - c0) * rb;
+            char *dst = (char *)P.out + ((size_t)trow * W + c0) * rb;
+            if ((rb & 3) == 0) {
+                for (int o = lane * 4; o < span; o += 128)
+                    *reinterpret_cast<uint32_t *>(dst + o) = *reinterpret_cast<const uint32_t *>(stage + o);
+            } else {
+                for (int o = lane; o < span; o += 32) dst[o] = stage[o];
+            }
+        }
+        __syncwarp();
+    } else if (p >= 0) {
+        copy_row((char *)P.out + (size_t)p * P.row_bytes, src, P.row_bytes, P.vec);
+    }
+}
+
+// Result of a point that has no neighbour (dead tiles; run-time k, no top-k list involved).
+template <typename T>
+__device__ __forceinline__ void emit_empty(const QueryParams &P, const IndexView<T> &ix, int64_t p, int trow, int tcol,
+                                           int lane, unsigned char *stage, bool valid)
+{
+    if (P.mode == PRS_EPI_INFO) {
+        if (p >= 0) {
+            const int k = P.k;
+            uint32_t *io = P.idx_out + (size_t)p * k;
+            T *dout = P.dist_out ? (T *)P.dist_out + (size_t)p * k : nullptr;
+            for (int i = 0; i < k; ++i) {
+                io[i] = ix.n_valid;
+                if (dout) dout[i] = Ar<T>::inf();
+            }
+            if (P.valid_out) P.valid_out[p] = valid ? 1 : 0;
+        }
+        if (P.flags) {
+            unsigned bad = __ballot_sync(0xffffffffu, p >= 0 && !valid);
+            if (lane == 0 && bad) atomicAdd(&P.flags[1], (unsigned)__popc(bad));
+        }
+    } else if (P.mode == PRS_EPI_NEAREST) {
+        emit_nearest(P, p, trow, tcol, lane, stage, PRS_NONE);
+    } else if (p >= 0) {
+        if (P.acc_f64)
+            gauss_empty<double>(P, p);
+        else
+            gauss_empty<float>(P, p);
+    }
+}
+
+// Result of a searched point.  All 32 lanes of the warp call this together.
+template <typename T, int K, int EPI>
+__device__ __forceinline__ void emit_result(const QueryParams &P, const IndexView<T> &ix, int64_t p, int trow, int tcol,
+                                            int lane, unsigned char *stage, const TopK<T, K> &top, bool valid)
+{
+    if (EPI == PRS_EPI_INFO) {
+        emit_info<T, K>(P, ix, p, lane, top, valid);
+    } else if (EPI == PRS_EPI_NEAREST) {
+        emit_nearest(P, p, trow, tcol, lane, stage, top.id[0]);
+    } else if (p >= 0) {
+        if (P.flags) {
+            bool kth = false;
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+                if (i == P.k - 1 && top.id[i] != PRS_NONE) kth = true;
+            if (kth && P.flags[0] == 0) P.flags[0] = 1;
+        }
+        if (!valid || top.id[0] == PRS_NONE) {
+            if (P.acc_f64)
+                gauss_empty<double>(P, p);
+            else
+                gauss_empty<float>(P, p);
+        } else if (P.acc_f64) {
+            if (P.data_f64)
+                gauss_epilogue<T, double, double, K>(P, ix, p, top);
+            else
+                gauss_epilogue<T, double, float, K>(P, ix, p, top);
+        } else {
+            gauss_epilogue<T, float, float, K>(P, ix, p, top);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ classification
+// One warp per tile: bound the tile's points by a spherical cap and ask the L2-resident coarse table whether ANY
+// source point lies within (cap + radius).  Tiles that see nothing ("dead") get their final result without a search
+// (fill value / "no neighbour" sentinels) - on wide target grids that is most of the output, written as a stream;
+// the other tiles are listed in live[] for the search kernel.
 
 // Cap (unit centre c, squared chord d2m) around the valid points of a tile; false when the tile has none.
 // Separable projections: the tile is the product of <= 32 longitudes (one per lane) and QROWS latitudes, and
@@ -921,6 +1119,7 @@ __device__ __forceinline__ bool tile_cap(const QueryParams &P, uint32_t tile, in
     return true;
 }
 
+// tile_live: can any point of the tile have a neighbour?  vmask = this lane's valid points (bit j = tile row j).
 template <typename T, int TK>
 __device__ __forceinline__ bool tile_live(const QueryParams &P, const IndexView<T> &ix, uint32_t tile, int lane,
                                           unsigned &vmask_out)
@@ -954,7 +1153,7 @@ __device__ __forceinline__ bool fill_is_pattern(const QueryParams &P, int TK)
 }
 
 // tile_fill: the result of a tile without neighbours.  vmask is only read when !fill_is_pattern().
-template <typename T, int K, int TK>
+template <typename T, int TK>
 __device__ __forceinline__ void tile_fill(const QueryParams &P, const IndexView<T> &ix, uint32_t tile, int lane,
                                           unsigned char *stage, unsigned vmask)
 {
@@ -997,43 +1196,19 @@ __device__ __forceinline__ void tile_fill(const QueryParams &P, const IndexView<
         }
         return;
     }
-    TopK<T, K> top;
-    top.init();
 #pragma unroll 1
     for (int j = 0; j < QROWS; ++j) {
         const int64_t p = tile_point(P, TK, tile, trow0, tcol, j, lane);
-        epilogue<T, K, TK>(P, ix, p, trow0 + j, tcol, lane, stage, top, (vmask >> j) & 1u);
+        emit_empty<T>(P, ix, p, trow0 + j, tcol, lane, stage, (vmask >> j) & 1u);
     }
-}
-
-// One live tile, one point per thread (warp w of the block takes row w of the tile).
-template <typename T, int K, int TK>
-__device__ __forceinline__ void query_tile(const QueryParams &P, const IndexView<T> &ix, uint32_t tile, int lane,
-                                           int warp, unsigned char *stage, T dub, float s2r, float sr)
-{
-    int trow, tcol;
-    tile_origin(P, TK, tile, lane, trow, tcol);
-    const int64_t p = tile_point(P, TK, tile, trow, tcol, warp, lane);
-    trow += warp;
-    T qx = 0, qy = 0, qz = 0;
-    bool valid = false;
-    if (p >= 0) {
-        if (TK != PRS_TK_AREA_SEP && P.target_xyz)
-            valid = load_target_xyz<T>(P.target_xyz, p, qx, qy, qz);  // classification has been here
-        else
-            valid = target_point<T, TK>(P, p, trow, tcol, qx, qy, qz);
-    }
-    TopK<T, K> top;
-    top.init();
-    if (valid) knn_search<T, K>(ix, qx, qy, qz, dub, s2r, sr, top);
-    epilogue<T, K, TK>(P, ix, p, trow, tcol, lane, stage, top, valid);
 }
 
 // Kernel A: classify each tile, fill the dead ones, list the live ones.  The fill stores (95 us of DRAM time on C2)
 // overlap the classification arithmetic of other warps inside this kernel.  Tried and rejected (slower on C1, C2,
 // C3 and C5, profiles/r1_overlap_experiments.txt): one persistent self-scheduling kernel doing classification and
 // search, and classification / fill / search as three kernels with the fill stream on a second stream.
-template <typename T, int K, int TK>
+// Independent of the number of neighbours: a dead tile's result is sentinels / fill whatever k is.
+template <typename T, int TK>
 __global__ void __launch_bounds__(QWARPS * 32, 4)
     classify_kernel(const __grid_constant__ QueryParams P, const __grid_constant__ IndexView<T> ix, uint32_t n_tiles,
                     uint32_t *__restrict__ live, uint32_t *__restrict__ n_live)
@@ -1049,25 +1224,172 @@ __global__ void __launch_bounds__(QWARPS * 32, 4)
             if (P.tile_row_live && TK != PRS_TK_LONLAT) P.tile_row_live[tile / (uint32_t)P.tiles_x] = 1;
         }
     } else {
-        tile_fill<T, K, TK>(P, ix, tile, lane, stage_all[warp], vmask);
+        tile_fill<T, TK>(P, ix, tile, lane, stage_all[warp], vmask);
     }
 }
 
-// Kernel B: the tiles that may have neighbours.  One block of QROWS warps per live tile, one point per thread.
-template <typename T, int K, int TK>
+// ------------------------------------------------------------------------------------------ search
+// Kernel B: the tiles that may have neighbours.  One block of QROWS warps per live tile, one point per thread
+// (warp w takes row w of the tile).  Per tile:
+//   1. every thread finds its point's home cell; the block reduces, per row of cells, the span of cells its 3x3
+//      blocks touch (StageCtx::umin / umax);
+//   2. warp 0 reads the bounds of those spans from the cell table, lays the runs out back to back in the staging
+//      buffer and fetches each with one bulk copy (cp.async.bulk -> mbarrier); meanwhile every thread reads the bounds
+//      of its own three runs;
+//   3. the threads scan their candidates from shared memory, prove the result with the closed-form cap bounds or
+//      continue in the general search (global memory), and write their result.
+// A tile whose points lie on different cube faces, span more than HULL_ROWS rows of cells or need more than the
+// staging buffer holds is searched straight from global memory (scan_home_global) - sparse targets like C2's
+// 5 km grid over a 1 km swath, where neighbouring points share no cells, always are.
+template <typename T, int K, int EPI>
 __global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS(K))
     query_kernel(const __grid_constant__ QueryParams P, const __grid_constant__ IndexView<T> ix,
                  const uint32_t *__restrict__ live, const uint32_t *__restrict__ n_live)
 {
-    __shared__ __align__(16) unsigned char stage_all[QROWS][32 * STAGE_ROW_BYTES];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];  // staged records [+ row stage of the nearest epilogue]
+    __shared__ StageCtx sc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    Rec<T> *srecs = reinterpret_cast<Rec<T> *>(dyn_smem);
+    unsigned char *stage = dyn_smem + PRS_STAGE_BYTES(K) + warp * (32 * STAGE_ROW_BYTES);  // EPI_NEAREST only
+    constexpr uint32_t CAP = PRS_STAGE_BYTES(K) / sizeof(Rec<T>);
     const uint32_t count = __ldg(n_live);
     const T dub = (T)(P.radius * P.radius);  // pykdtree: dtype(distance_upper_bound ** 2)
     const float s2r = cap_s2<T>(dub), sr = sqrtf(s2r);
+    const int TKr = P.tk;
+    if (tid == 0) mbar_init(reinterpret_cast<uint64_t *>(&sc.bar), 32);
+    uint32_t phase = 0;
 #pragma unroll 1
     for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) {
         const uint32_t tile = __ldg(live + t);
-        query_tile<T, K, TK>(P, ix, tile, lane, warp, stage_all[warp], dub, s2r, sr);
+        int trow, tcol;
+        tile_origin(P, TKr, tile, lane, trow, tcol);
+        const int64_t p = tile_point(P, TKr, tile, trow, tcol, warp, lane);
+        trow += warp;
+        T qx = 0, qy = 0, qz = 0;
+        bool valid = false;
+        if (p >= 0) valid = query_point<T>(P, p, trow, tcol, qx, qy, qz);
+        Home h;
+        h.face = 0, h.cu = h.cv = 0;
+        h.hb.u0 = h.hb.v0 = 1, h.hb.u1 = h.hb.v1 = 0;
+        if (valid) h = home_of<T>(ix, qx, qy, qz);
+        const bool has_block = valid && h.hb.u0 <= h.hb.u1;
+        // ---- 1. hull of the tile's home blocks
+        if (tid < HULL_ROWS) {
+            sc.umin[tid] = 0x7fffffff;
+            sc.umax[tid] = -1;
+        }
+        if (tid == 0) {
+            sc.vlo = 0x7fffffff;
+            sc.vhi = -1;
+            sc.faces = 0;
+        }
+        __syncthreads();  // also: every thread is done with the previous tile's staged records
+        {
+            unsigned todo = __ballot_sync(0xffffffffu, has_block);
+            if (todo) {
+                const int wlo = __reduce_min_sync(0xffffffffu, has_block ? h.hb.v0 : 0x7fffffff);
+                const int whi = __reduce_max_sync(0xffffffffu, has_block ? h.hb.v1 : -1);
+                const unsigned wf = __reduce_or_sync(0xffffffffu, has_block ? 1u << h.face : 0u);
+                if (lane == 0) {
+                    atomicMin(&sc.vlo, wlo);
+                    atomicMax(&sc.vhi, whi);
+                    atomicOr(&sc.faces, wf);
+                }
+            }
+            // lanes with the same home row contribute one span; rows v0..v1 of the block all take it
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                const int v = __shfl_sync(0xffffffffu, h.cv, src);
+                const bool mine = has_block && h.cv == v;
+                const unsigned grp = __ballot_sync(0xffffffffu, mine);
+                const int lo = __reduce_min_sync(0xffffffffu, mine ? h.hb.u0 : 0x7fffffff);
+                const int hi = __reduce_max_sync(0xffffffffu, mine ? h.hb.u1 : -1);
+                const int r0 = __shfl_sync(0xffffffffu, h.hb.v0, src), r1 = __shfl_sync(0xffffffffu, h.hb.v1, src);
+                if (lane < 3 && r0 + lane <= r1) {
+                    atomicMin(&sc.umin[(r0 + lane) & (HULL_ROWS - 1)], lo);
+                    atomicMax(&sc.umax[(r0 + lane) & (HULL_ROWS - 1)], hi);
+                }
+                todo &= ~grp;
+            }
+        }
+        // the bounds of this thread's own runs do not depend on the staging: their loads overlap steps 1 and 2
+        HomeRuns hr;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) hr.s[j] = hr.e[j] = 0, hr.v[j] = 0;
+        if (has_block) hr = home_runs<T>(ix, h);
+        __syncthreads();
+        // ---- 2. warp 0 lays out and fetches the rows
+        if (warp == 0) {
+            const int vlo = sc.vlo, vhi = sc.vhi;
+            const unsigned faces = sc.faces;
+            bool ok = vhi >= vlo && (vhi - vlo) < HULL_ROWS && __popc(faces) == 1;
+            uint32_t gs[2] = {0, 0}, n[2] = {0, 0};
+            if (ok) {
+                const int face = __ffs(faces) - 1;
+                const FaceTable &ft = ix.fine;
+                const int fw = ft.fw[face];
+                const uint32_t *row0 = ix.cell_start + ft.base[face] - (int64_t)ft.fv0[face] * fw - ft.fu0[face];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int v = vlo + lane + 32 * j;
+                    if (v <= vhi) {
+                        const int slot = v & (HULL_ROWS - 1);
+                        const int u0 = sc.umin[slot], u1 = sc.umax[slot];
+                        if (u1 >= u0) {
+                            const uint32_t *row = row0 + (int64_t)v * fw;
+                            gs[j] = __ldg(row + u0);
+                            n[j] = __ldg(row + u1 + 1) - gs[j];
+                        }
+                    }
+                }
+            }
+            // exclusive prefix over the (up to 64) rows: lanes hold rows lane and lane + 32
+            uint32_t a = n[0], b = n[1];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
+                if (lane >= o) a += ta, b += tb;
+            }
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, a, 31), total = tot0 + __shfl_sync(0xffffffffu, b, 31);
+            ok = ok && total > 0 && total <= CAP;
+            if (ok) {
+                const uint32_t base[2] = {a - n[0], tot0 + b - n[1]};
+                fence_proxy_async();  // the buffer was read (generic proxy) for the previous tile
+                mbar_arrive_expect_tx(reinterpret_cast<uint64_t *>(&sc.bar), (n[0] + n[1]) * (uint32_t)sizeof(Rec<T>));
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int v = vlo + lane + 32 * j;
+                    if (v <= vhi) {
+                        const int slot = v & (HULL_ROWS - 1);
+                        sc.gstart[slot] = gs[j];
+                        sc.sbase[slot] = base[j];
+                        if (n[j])
+                            bulk_copy_g2s(srecs + base[j], ix.recs + gs[j], n[j] * (uint32_t)sizeof(Rec<T>),
+                                          reinterpret_cast<uint64_t *>(&sc.bar));
+                    }
+                }
+            }
+            // written here and nowhere else: a thread that is slow to read it cannot see the next tile's value,
+            // because warp 0 only gets here again after two more block-wide barriers
+            if (lane == 0) sc.staged = ok ? 1 : 0;
+        }
+        __syncthreads();
+        // ---- 3. search
+        TopK<T, K> top;
+        top.init();
+        const bool staged = sc.staged != 0;
+        if (staged) {
+            mbar_wait(reinterpret_cast<uint64_t *>(&sc.bar), phase);
+            phase ^= 1u;
+        }
+        if (valid) {
+            if (staged)
+                scan_home_staged<T, K>(sc, srecs, hr, qx, qy, qz, dub, top);
+            else
+                scan_home_global<T, K>(ix, hr, qx, qy, qz, dub, top);
+            knn_finish<T, K>(ix, h, qx, qy, qz, dub, s2r, sr, top);
+        }
+        emit_result<T, K, EPI>(P, ix, p, trow, tcol, lane, stage, top, valid);
     }
 }
 

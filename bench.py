@@ -270,7 +270,7 @@ class Resident(object):
         self.q_events, self.b_events = [], []
         self.weight_funcs = [custom_weight] * self.channels if self.channels > 1 else custom_weight
 
-    def step(self, record=False):
+    def step(self, record=False, want_info=False):
         from pyresample_b200 import _cabi, kd_tree
         torch, L = self.torch, _cabi.lib()
         ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -290,26 +290,29 @@ class Resident(object):
             stream = kd_tree._stream()
             if self.mode == "nearest":
                 out = torch.empty((n_t, channels), dtype=data_dev.dtype, device="cuda")
-                _cabi.check(L.prs_resample_nearest(source.index.handle, ctypes.byref(tg), float(self.radius),
+                _cabi.check(L.prs_resample_nearest(source.handle, ctypes.byref(tg), float(self.radius),
                                                    kd_tree._ptr(data_dev), channels * data_dev.element_size(),
                                                    kd_tree._ptr(self.fill), kd_tree._ptr(out), stream))
             else:
                 acc = torch.float64 if channels > 1 else torch.float32
                 out = torch.empty((n_t, channels), dtype=acc, device="cuda")
                 sig = (ctypes.c_double * channels)(*([self.cfg.get("sigma", 25000.0)] * channels))
-                _cabi.check(L.prs_resample_gauss(source.index.handle, ctypes.byref(tg), int(self.k),
+                _cabi.check(L.prs_resample_gauss(source.handle, ctypes.byref(tg), int(self.k),
                                                  float(self.radius), kd_tree._ptr(data_dev), 0, channels, sig, 0.0,
                                                  kd_tree._ptr(out), None, None, None, stream))
         e2.record()
         if record:
             self.b_events.append((e0, e1))
             self.q_events.append((e1, e2))
-        self.info = {"n_valid": int(source.n_valid), "n_indexed": int(source.index.n_indexed),
-                     "cells_per_side": int(source.index.cells_per_side), "index_bytes": int(source.index.bytes)}
+        if want_info:  # reading the index description makes the host wait for the build: last step only
+            self.info = {"n_valid": int(source.n_valid), "n_indexed": int(source.index.n_indexed),
+                         "cells_per_side": int(source.index.cells_per_side), "index_bytes": int(source.index.bytes)}
         return out
 
     def out_itemsize(self):
-        return 8 if (self.mode != "nearest" and self.channels > 1) else self.data_dev.element_size()
+        if self.mode != "nearest" and self.channels > 1:
+            return 8
+        return self.data_dev.element_size() if self.data_dev is not None else self.data_itemsize
 
     def timed(self, steps, warmup, sync_all, sampler=None):
         """W warm-up steps, then exactly K timed steps; returns (ms_per_step list pieces, launches)."""
@@ -324,8 +327,8 @@ class Resident(object):
         launches0 = L.prs_launch_count()
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_start.record()
-        for _ in range(steps):
-            out = self.step(record=True)
+        for i in range(steps):
+            out = self.step(record=True, want_info=(i == steps - 1))
         t_end.record()
         sync_all()
         del out
@@ -337,7 +340,7 @@ class Resident(object):
 
     def roofline(self, q_all, b_ms, peak, peak_kind, traffic):
         n_t_rank = self.rows[1] * self.W
-        itemsize = self.data_dev.element_size()
+        itemsize = self.data_dev.element_size() if self.data_dev is not None else self.data_itemsize
         q_ms = float(np.mean(q_all))
         b_alg = algorithmic_bytes(self.info["n_indexed"], n_t_rank, self.channels, 4, itemsize, self.out_itemsize())
         achieved = b_alg / (q_ms * 1e-3) / 1e9
@@ -525,7 +528,9 @@ def main():
     extra = {}
     if args.config != 5 and not args.no_extra_configs and args.scale == 1.0:
         del wl.dev, dev
+        data_itemsize = wl.data_dev.element_size()
         wl.data_dev = wl.source_dev = None
+        wl.data_itemsize = data_itemsize
         torch.cuda.empty_cache()
         w5 = Resident(5, 1.0, rank, world)
         n5 = max(3, min(args.steps, 10))
@@ -589,6 +594,8 @@ def time_xarray_nn(cfg, radius, k):
             def __init__(self, data, dims=None, coords=None, attrs=None):
                 self.data, self.dims, self.coords, self.attrs = data, tuple(dims), dict(coords or {}), dict(attrs or {})
             shape = property(lambda s: s.data.shape)
+            ndim = property(lambda s: s.data.ndim)
+            __getitem__ = lambda s, key: s.data[key]  # noqa: E731
             dtype = property(lambda s: s.data.dtype)
             sizes = property(lambda s: dict(zip(s.dims, s.data.shape)))
         kd_tree.DataArray = _DA

@@ -71,9 +71,9 @@ def needs_rebuild():
 
 
 # search kernels: (tree dtype, top-k width K, epilogue) with epilogue 0 = neighbour info, 1 = nearest gather (K = 1),
-# 2 = Gaussian weighting
+# 2 / 3 / 4 = Gaussian weighting with float32 / float64-over-float32-data / float64 accumulation
 _QUERY_INSTANCES = [(t, k, e) for t in ("float", "double") for k, e in
-                    [(1, 0), (4, 0), (8, 0), (16, 0), (32, 0), (1, 1), (4, 2), (8, 2), (16, 2), (32, 2)]]
+                    [(1, 0), (4, 0), (8, 0), (16, 0), (32, 0), (1, 1)] + [(k, e) for e in (2, 3, 4) for k in (4, 8, 16, 32)]]
 
 
 def build(force=False, verbose=False, jobs=None):

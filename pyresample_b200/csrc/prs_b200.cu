@@ -5,6 +5,7 @@
 
 #include <vector>
 
+#define PRS_WITH_INDEX_BUILD
 #include "prs_common.cuh"
 #include "prs_index.cuh"
 #include "prs_proj.cuh"
@@ -232,10 +233,10 @@ struct TargetTables {
 namespace prs {
 // launch_search<T, K, EPI> / launch_classify<T> are instantiated in prs_query_inst.cu / prs_classify_inst.cu, never here
 #define PRS_EXTERN_SEARCH(T, K, EPI)                                                                                   \
-    extern template int launch_search<T, K, EPI>(const QueryParams &, const IndexView<T> &, int64_t, const uint32_t *, \
+    extern template int launch_search<T, K, EPI>(const QueryParams &, const IndexRef<T> &, int64_t, const uint32_t *, \
                                                  const uint32_t *, cudaStream_t);
 #define PRS_EXTERN_T(T)                                                                                              \
-    extern template int launch_classify<T>(const QueryParams &, const IndexView<T> &, int64_t, uint32_t *, uint32_t *, \
+    extern template int launch_classify<T>(const QueryParams &, const IndexRef<T> &, int64_t, uint32_t *, uint32_t *, \
                                            cudaStream_t);                                                            \
     extern template int launch_coverage_t<T>(const QueryParams &, int, uint8_t *, cudaStream_t);                     \
     PRS_EXTERN_SEARCH(T, 1, PRS_EPI_INFO)                                                                            \
@@ -244,16 +245,24 @@ namespace prs {
     PRS_EXTERN_SEARCH(T, 16, PRS_EPI_INFO)                                                                           \
     PRS_EXTERN_SEARCH(T, 32, PRS_EPI_INFO)                                                                           \
     PRS_EXTERN_SEARCH(T, 1, PRS_EPI_NEAREST)                                                                         \
-    PRS_EXTERN_SEARCH(T, 4, PRS_EPI_GAUSS)                                                                           \
-    PRS_EXTERN_SEARCH(T, 8, PRS_EPI_GAUSS)                                                                           \
-    PRS_EXTERN_SEARCH(T, 16, PRS_EPI_GAUSS)                                                                          \
-    PRS_EXTERN_SEARCH(T, 32, PRS_EPI_GAUSS)
+    PRS_EXTERN_SEARCH(T, 4, PRS_EPI_GAUSS_FF)                                                                        \
+    PRS_EXTERN_SEARCH(T, 8, PRS_EPI_GAUSS_FF)                                                                        \
+    PRS_EXTERN_SEARCH(T, 16, PRS_EPI_GAUSS_FF)                                                                       \
+    PRS_EXTERN_SEARCH(T, 32, PRS_EPI_GAUSS_FF)                                                                       \
+    PRS_EXTERN_SEARCH(T, 4, PRS_EPI_GAUSS_DF)                                                                        \
+    PRS_EXTERN_SEARCH(T, 8, PRS_EPI_GAUSS_DF)                                                                        \
+    PRS_EXTERN_SEARCH(T, 16, PRS_EPI_GAUSS_DF)                                                                       \
+    PRS_EXTERN_SEARCH(T, 32, PRS_EPI_GAUSS_DF)                                                                       \
+    PRS_EXTERN_SEARCH(T, 4, PRS_EPI_GAUSS_DD)                                                                        \
+    PRS_EXTERN_SEARCH(T, 8, PRS_EPI_GAUSS_DD)                                                                        \
+    PRS_EXTERN_SEARCH(T, 16, PRS_EPI_GAUSS_DD)                                                                       \
+    PRS_EXTERN_SEARCH(T, 32, PRS_EPI_GAUSS_DD)
 PRS_EXTERN_T(float)
 PRS_EXTERN_T(double)
 
 // Dispatch on (K, epilogue).  The top-k list width K is the smallest instantiated one >= k.
 template <typename T>
-int launch_search_k(const QueryParams &P, const IndexView<T> &ix, int64_t tiles, const uint32_t *live,
+int launch_search_k(const QueryParams &P, const IndexRef<T> &ix, int64_t tiles, const uint32_t *live,
                     const uint32_t *n_live, cudaStream_t st)
 {
     const int k = P.k;
@@ -263,10 +272,19 @@ int launch_search_k(const QueryParams &P, const IndexView<T> &ix, int64_t tiles,
     case PRS_EPI_NEAREST:
         PRS_GO(1, PRS_EPI_NEAREST);
     case PRS_EPI_GAUSS:
-        if (k <= 4) PRS_GO(4, PRS_EPI_GAUSS);
-        if (k <= 8) PRS_GO(8, PRS_EPI_GAUSS);
-        if (k <= 16) PRS_GO(16, PRS_EPI_GAUSS);
-        PRS_GO(32, PRS_EPI_GAUSS);
+#define PRS_GO_K(EPI)             \
+    if (k <= 4) PRS_GO(4, EPI);   \
+    if (k <= 8) PRS_GO(8, EPI);   \
+    if (k <= 16) PRS_GO(16, EPI); \
+    PRS_GO(32, EPI)
+        if (!P.acc_f64) {
+            PRS_GO_K(PRS_EPI_GAUSS_FF);
+        } else if (!P.data_f64) {
+            PRS_GO_K(PRS_EPI_GAUSS_DF);
+        } else {
+            PRS_GO_K(PRS_EPI_GAUSS_DD);
+        }
+#undef PRS_GO_K
     default:
         if (k <= 1) PRS_GO(1, PRS_EPI_INFO);
         if (k <= 4) PRS_GO(4, PRS_EPI_INFO);
@@ -340,17 +358,12 @@ inline size_t live_list_bytes(int64_t tiles) { return ((size_t)(tiles + 1) * siz
 
 template <typename T> int launch_query_t(QueryParams &P, const prs_index *index, const prs_target *tg, cudaStream_t st)
 {
-    IndexView<T> ix;
-    ix.recs = index->n_indexed > 0 ? (const Rec<T> *)index->recs : nullptr;
+    IndexRef<T> ix;
+    ix.recs = (const Rec<T> *)index->recs;
     ix.cell_start = index->cell_start;
     ix.coarse_start = index->coarse_start;
     ix.rank = index->rank;
-    ix.fine = index->fine;
-    ix.coarse = index->coarse;
-    ix.G = index->G;
-    ix.Gc = index->Gc;
-    ix.n_valid = (uint32_t)index->n_valid;
-    ix.first_valid_source = index->first_valid_source;
+    ix.meta = index->meta_dev;
     int tk = PRS_TK_LONLAT;
     TargetTables tabs;
     int rc = setup_target<T>(P, tg, tk, tabs, st);
@@ -494,8 +507,8 @@ int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, uint
     cudaStream_t st = (cudaStream_t)stream;
     if (!index_out) return fail(PRS_EINVAL, "index_out is null");
     if (n <= 0 || n >= 0xFFFFFFFFLL) return fail(PRS_EINVAL, "source size must be in [1, 2^32 - 2]");
-    if (dtype != tree_dtype)
-        return fail(PRS_ENOSUP, "lon/lat dtype must equal tree dtype (cast on the host side of the ABI)");
+    if (dtype != tree_dtype && !(dtype == PRS_F32 && tree_dtype == PRS_F64))
+        return fail(PRS_ENOSUP, "lon/lat dtype must equal the tree dtype, or be float32 for a float64 tree");
     if (!valid && !(flags & PRS_BUILD_COMPUTE_VALID))
         return fail(PRS_EINVAL, "valid mask is required (prs_valid_mask) unless PRS_BUILD_COMPUTE_VALID is set");
     if ((flags & PRS_BUILD_RANKS) && !valid) return fail(PRS_EINVAL, "PRS_BUILD_RANKS needs the valid mask buffer");
@@ -504,13 +517,18 @@ int prs_index_build(const void *lon, const void *lat, int64_t n, int dtype, uint
     ix->uses = new prs_index_uses();
     ix->tree_dtype = tree_dtype;
     ix->n_source = n;
-    int rc;
-    if (tree_dtype == PRS_F32)
-        rc = index_build_t<float>((const float *)lon, (const float *)lat, n, valid, box, premask, exclude, cover, flags,
-                                  k_hint, radius_hint, ix, st);
+    int rc = PRS_OK;
+    if (cudaEventCreateWithFlags(&ix->planned, cudaEventDisableTiming) != cudaSuccess)
+        rc = fail(PRS_ECUDA, "cudaEventCreate failed");
+    else if (tree_dtype == PRS_F32)
+        rc = index_build_t<float, float>((const float *)lon, (const float *)lat, n, valid, box, premask, exclude, cover,
+                                         flags, k_hint, radius_hint, ix, st);
+    else if (tree_dtype == PRS_F64 && dtype == PRS_F64)
+        rc = index_build_t<double, double>((const double *)lon, (const double *)lat, n, valid, box, premask, exclude,
+                                           cover, flags, k_hint, radius_hint, ix, st);
     else if (tree_dtype == PRS_F64)
-        rc = index_build_t<double>((const double *)lon, (const double *)lat, n, valid, box, premask, exclude, cover, flags,
-                                   k_hint, radius_hint, ix, st);
+        rc = index_build_t<float, double>((const float *)lon, (const float *)lat, n, valid, box, premask, exclude,
+                                          cover, flags, k_hint, radius_hint, ix, st);
     else
         rc = fail(PRS_EINVAL, "tree_dtype must be PRS_F32 or PRS_F64");
     if (rc != PRS_OK) {
@@ -559,6 +577,8 @@ int prs_index_destroy(prs_index *ix)
     if (ix->cell_alloc) cudaFreeAsync(ix->cell_alloc, ix->stream);
     if (ix->coarse_alloc) cudaFreeAsync(ix->coarse_alloc, ix->stream);
     if (ix->rank) cudaFreeAsync(ix->rank, ix->stream);
+    if (ix->meta_dev) cudaFreeAsync(ix->meta_dev, ix->stream);
+    if (ix->planned) cudaEventDestroy(ix->planned);
     delete ix;
     return PRS_OK;
 }
@@ -566,14 +586,18 @@ int prs_index_destroy(prs_index *ix)
 int prs_index_info(const prs_index *ix, int64_t info[8])
 {
     if (!ix || !info) return fail(PRS_EINVAL, "null argument");
+    // the build never waits for the device: the numbers are fetched (a copy that only waits for the plan kernel)
+    // the first time somebody asks
+    int rc = index_fetch_meta(ix);
+    if (rc != PRS_OK) return rc;
     info[0] = ix->n_source;
-    info[1] = ix->n_valid;
-    info[2] = ix->n_indexed;
-    info[3] = ix->G;
+    info[1] = ix->meta.n_valid;
+    info[2] = ix->meta.n_indexed;
+    info[3] = ix->meta.G;
     info[4] = (int64_t)ix->bytes;
     info[5] = ix->tree_dtype;
-    info[6] = ix->Gc;
-    info[7] = ix->all_valid;
+    info[6] = ix->meta.Gc;
+    info[7] = ix->meta.all_valid;
     return PRS_OK;
 }
 
@@ -590,8 +614,12 @@ int prs_query(const prs_index *index, const prs_target *target, int k, double ra
     P.dist_out = dist_out;
     P.valid_out = valid_out;
     if (!idx_out) return fail(PRS_EINVAL, "idx_out is null");
-    if (index && !index->all_valid && !index->rank && index->n_valid > 0)
-        return fail(PRS_EINVAL, "prs_query needs an index built with PRS_BUILD_RANKS (some source points are invalid)");
+    if (index && !index->rank) {  // without the rank table index_array is only right when every source point is valid
+        int rc0 = index_fetch_meta(index);
+        if (rc0 != PRS_OK) return rc0;
+        if (!index->meta.all_valid && index->meta.n_valid > 0)
+            return fail(PRS_EINVAL, "prs_query needs an index built with PRS_BUILD_RANKS (some source points are invalid)");
+    }
     if (flags_host) {
         PRS_CK(cudaMallocAsync((void **)&P.flags, 2 * sizeof(unsigned int), st));
         PRS_CK(cudaMemsetAsync(P.flags, 0, 2 * sizeof(unsigned int), st));

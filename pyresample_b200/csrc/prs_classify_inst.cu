@@ -7,7 +7,7 @@
 #endif
 
 namespace prs {
-template int launch_classify<PRS_INST_T>(const QueryParams &, const IndexView<PRS_INST_T> &, int64_t, uint32_t *, uint32_t *,
+template int launch_classify<PRS_INST_T>(const QueryParams &, const IndexRef<PRS_INST_T> &, int64_t, uint32_t *, uint32_t *,
                                          cudaStream_t);
 template int launch_coverage_t<PRS_INST_T>(const QueryParams &, int, uint8_t *, cudaStream_t);
 }

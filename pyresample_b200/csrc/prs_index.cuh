@@ -29,29 +29,45 @@ struct FaceTable {
     int64_t base[6];
 };
 
+// Description of a built index.  It lives in DEVICE memory (written by build_plan_kernel, read by every later build
+// pass and by the query kernels), so that the build is queued without a host round trip; the host fetches a copy
+// only when somebody asks (prs_index_info).
+struct IndexMeta {
+    uint32_t n_valid;             // valid source points (pykdtree's .n)
+    uint32_t n_skipped;           // valid but excluded (query mask) or outside this rank's target coverage
+    uint32_t first_valid_source;  // raveled index of rank 0 (kd_tree.py:754-759 gathers new_data[0] for missing)
+    uint32_t n_occ;               // occupied probe cells
+    int32_t G, Gc;                // fine / coarse cells per face side (G a multiple of COARSE)
+    int32_t all_valid;            // rank == source index
+    int32_t status;               // 0 ok; 1: the cell table did not fit its allocation even at the coarsest grid
+    int64_t n_indexed;            // valid and not skipped
+    int64_t n_cells, n_coarse;
+    int64_t n_source;
+    FaceTable fine, coarse;
+};
+
 }  // namespace prs
+
+struct prs_index_uses;
 
 struct prs_index {
     int tree_dtype;      // PRS_F32 / PRS_F64
     int64_t n_source;    // raveled source size
-    int64_t n_valid;     // pykdtree's .n : number of valid source points (rank space size)
-    int64_t n_indexed;   // valid and not excluded
-    int G;               // fine cells per face side (multiple of COARSE)
-    int Gc;              // coarse cells per face side
-    int all_valid;       // rank == source index
-    uint32_t first_valid_source;  // raveled index of rank 0 (kd_tree.py:754-759 gathers new_data[0] for missing)
-    void *recs;
+    void *recs;          // capacity n_source records
     uint32_t *cell_start;    // = cell_alloc + 3
     uint32_t *coarse_start;  // = coarse_alloc + 3
     uint32_t *cell_alloc, *coarse_alloc;
-    uint32_t *rank;
-    prs::FaceTable fine, coarse;
-    int64_t n_cells, n_coarse;
+    uint32_t *rank;      // only with PRS_BUILD_RANKS
+    int64_t cap_cells, cap_coarse;
+    prs::IndexMeta *meta_dev;
+    prs::IndexMeta meta;  // host copy, valid once `fetched`
+    int fetched;
+    cudaEvent_t planned;  // recorded behind build_plan_kernel: meta_dev is final from there on
     size_t bytes;
     cudaStream_t stream;  // stream the memory was allocated on (stream-ordered free)
     // queries launched on OTHER streams: one event per stream, recorded behind the stream's latest query, so that
     // prs_index_destroy can order the stream-ordered free behind them (see index_note_use / prs_index_destroy)
-    struct prs_index_uses *uses;
+    prs_index_uses *uses;
 };
 
 struct prs_index_uses {
@@ -125,68 +141,36 @@ template <typename T> __device__ __forceinline__ void unit_f32(T x, T y, T z, fl
     fz = (float)z * invR;
 }
 
-// Read-back of a few words: cudaMemcpyAsync + cudaStreamSynchronize by default.  Optional low-latency variant
-// (PRS_MAILBOX=1): a one-warp kernel copies them into mapped pinned host memory and raises a sequence flag, the
-// host spins on the flag.
-static __global__ void publish_kernel(const uint32_t *__restrict__ src, volatile uint32_t *dst, int n_words, uint32_t seq)
-{
-    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[1 + i] = src[i];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) dst[0] = seq;
-}
+#ifdef PRS_WITH_INDEX_BUILD  // the build itself is only compiled into prs_b200.cu
+struct BuildCounters {
+    uint32_t n_valid;    // unused by the kernels (block totals are reduced by build_plan_kernel)
+    uint32_t n_skipped;
+    uint32_t first_inv;  // ~(raveled index of the first valid point), 0 = none: raised with atomicMax from a zeroed word
+    uint32_t pad;
+};
 
-inline int read_back_small(const void *dev_src, void *host_dst, size_t bytes, cudaStream_t st)
+// Host copy of the index description, fetched on first use: a copy on a side stream that only waits for the plan
+// kernel (not for whatever was queued behind the build).
+inline int index_fetch_meta(const prs_index *cix)
 {
-    struct Mailbox {
-        volatile uint32_t *host = nullptr;
-        uint32_t *dev = nullptr;
-        uint32_t seq = 0;
-    };
-    static thread_local Mailbox mb;
-    const int n_words = (int)((bytes + 3) / 4);
-    // opt-in (PRS_MAILBOX=1): it saves ~10 us per build, but with NVML clock queries running next to it (bench.py's
-    // sampler, any monitoring agent) the flag write was seen to arrive tens of milliseconds late
-    static const bool mailbox_enabled = [] {
-        const char *e = getenv("PRS_MAILBOX");
-        return e && e[0] == '1';
-    }();
-    const bool use_mailbox = n_words <= 255 && mailbox_enabled;
-    if (use_mailbox && !mb.host) {
-        void *h = nullptr;
-        if (cudaHostAlloc(&h, 1024, cudaHostAllocMapped) == cudaSuccess &&
-            cudaHostGetDevicePointer((void **)&mb.dev, h, 0) == cudaSuccess) {
-            mb.host = (volatile uint32_t *)h;
-            mb.host[0] = 0;
-        } else {
-            cudaGetLastError();
-        }
-    }
-    if (use_mailbox && mb.host) {
-        const uint32_t seq = ++mb.seq ? mb.seq : ++mb.seq;  // never 0
-        publish_kernel<<<1, 64, 0, st>>>((const uint32_t *)dev_src, mb.dev, n_words, seq);
-        PRS_CKL();
-        // spin (bounded), then fall back to a blocking wait so that an error cannot hang the host
-        for (long spins = 0; mb.host[0] != seq; ++spins) {
-            if (spins > 20000000L) {
-                PRS_CK(cudaStreamSynchronize(st));
-                if (mb.host[0] != seq) return fail(PRS_ECUDA, "index build: read-back flag never arrived");
-            }
-        }
-        memcpy(host_dst, (const void *)(mb.host + 1), bytes);
-        return PRS_OK;
-    }
-    PRS_CK(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, st));
-    PRS_CK(cudaStreamSynchronize(st));
+    prs_index *ix = const_cast<prs_index *>(cix);
+    if (!ix) return fail(PRS_EINVAL, "null index");
+    if (ix->fetched) return PRS_OK;
+    static std::mutex lock;
+    static cudaStream_t side[64] = {nullptr};
+    std::lock_guard<std::mutex> guard(lock);
+    if (ix->fetched) return PRS_OK;
+    int dev = 0;
+    PRS_CK(cudaGetDevice(&dev));
+    const int slot = dev < 0 || dev >= 64 ? 0 : dev;
+    if (!side[slot]) PRS_CK(cudaStreamCreateWithFlags(&side[slot], cudaStreamNonBlocking));
+    PRS_CK(cudaStreamWaitEvent(side[slot], ix->planned, 0));
+    PRS_CK(cudaMemcpyAsync(&ix->meta, ix->meta_dev, sizeof(IndexMeta), cudaMemcpyDeviceToHost, side[slot]));
+    PRS_CK(cudaStreamSynchronize(side[slot]));
+    ix->fetched = 1;
+    if (ix->meta.status != 0) return fail(PRS_ENOSUP, "cell table too large for its allocation");
     return PRS_OK;
 }
-
-struct BuildCounters {
-    uint32_t n_valid;       // valid source points (pykdtree's .n)
-    uint32_t n_skipped;     // valid but excluded (query mask) or outside this rank's target coverage
-    uint32_t first_source;  // raveled index of the first valid point (rank 0)
-    uint32_t n_occ;         // occupied probe cells
-};
 
 // _get_valid_input_index (kd_tree.py:406, 426-428) and the reduce_data box of data_reduce.py:282-305.  numpy promotes
 // float32 coordinates to float64 against the float64 bounds; float64 conversions and compares are slow on the
@@ -348,11 +332,11 @@ constexpr int BUILD_ITEMS = 4;  // points per thread in the build passes
 //                               this rank
 // Only approximate coordinates (fast sin/cos intrinsics) are needed here: probe and coverage cells are tens of
 // kilometres wide and both masks carry a whole cell of slack.  The exact ECEF transform runs in pass 2, for the
-// points that are kept, once the cell size is known.
-template <typename T>
+// points that are kept, once the cell size is known.  Tin: dtype of the lon/lat arrays.
+template <typename Tin>
 __global__ void __launch_bounds__(BUILD_TPB, PRS_SELECT_MIN_BLOCKS)
-    build_select_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, uint8_t *__restrict__ valid,
-                        int compute_valid, const BoxT<T> box, const uint8_t *__restrict__ premask,
+    build_select_kernel(const Tin *__restrict__ lon, const Tin *__restrict__ lat, int64_t n, uint8_t *__restrict__ valid,
+                        int compute_valid, const BoxT<Tin> box, const uint8_t *__restrict__ premask,
                         const uint8_t *__restrict__ exclude, const uint8_t *__restrict__ cover,
                         uint8_t *__restrict__ keep, uint8_t *__restrict__ occ, BuildCounters *counters,
                         uint2 *__restrict__ block_counts)
@@ -362,7 +346,7 @@ __global__ void __launch_bounds__(BUILD_TPB, PRS_SELECT_MIN_BLOCKS)
     const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * BUILD_ITEMS) + threadIdx.x;
     int nv = 0, ns = 0;
     uint32_t first = 0xFFFFFFFFu;
-    T lo[BUILD_ITEMS], la[BUILD_ITEMS];
+    Tin lo[BUILD_ITEMS], la[BUILD_ITEMS];
     uint8_t vin[BUILD_ITEMS], ex[BUILD_ITEMS];
 #pragma unroll
     for (int j = 0; j < BUILD_ITEMS; ++j) {
@@ -384,7 +368,7 @@ __global__ void __launch_bounds__(BUILD_TPB, PRS_SELECT_MIN_BLOCKS)
     for (int j = 0; j < BUILD_ITEMS; ++j) {
         const int64_t i = base + (int64_t)j * BUILD_TPB;
         if (i >= n) continue;
-        const bool v = compute_valid ? valid_predicate<T>(lo[j], la[j], box, vin[j] != 0) : vin[j] != 0;
+        const bool v = compute_valid ? valid_predicate<Tin>(lo[j], la[j], box, vin[j] != 0) : vin[j] != 0;
         if (compute_valid && valid) valid[i] = v ? 1 : 0;
         bool kept = false;
         if (v) {
@@ -436,7 +420,7 @@ __global__ void __launch_bounds__(BUILD_TPB, PRS_SELECT_MIN_BLOCKS)
         }
         keep[i] = kept ? 1 : 0;
     }
-    // block totals (one record per block, reduced by build_reduce_kernel: no same-address atomics storm)
+    // block totals (one record per block, reduced by build_plan_kernel: no same-address atomics storm)
     __shared__ int s_nv[BUILD_TPB / 32], s_ns[BUILD_TPB / 32];
     __shared__ uint32_t s_first[BUILD_TPB / 32];
 #pragma unroll
@@ -461,27 +445,76 @@ __global__ void __launch_bounds__(BUILD_TPB, PRS_SELECT_MIN_BLOCKS)
         }
         block_counts[blockIdx.x] = make_uint2((unsigned)tv, (unsigned)ts);
         // rank 0's source index: blocks run roughly in order, so almost all of them skip the atomic
-        if (tf < *(volatile uint32_t *)&counters->first_source) atomicMin(&counters->first_source, tf);
+        if (tf != 0xFFFFFFFFu && ~tf > *(volatile uint32_t *)&counters->first_inv) atomicMax(&counters->first_inv, ~tf);
     }
 }
 
-// Reduce the per-block counts and the occupancy probe: number of valid / skipped points, bounding rectangle (in
-// probe cells) of the occupied probe cells of each face (rect[f] = {u0, v0, u1, v1}) and their number.
-static __global__ void build_reduce_kernel(const uint8_t *__restrict__ occ, const uint2 *__restrict__ block_counts,
-                                           int64_t n_blocks, int *__restrict__ rect, BuildCounters *counters)
+struct PlanParams {
+    int64_t n, n_blocks, cap_cells;
+    double lambda;  // target points per cell
+    int g_max;      // upper limit of cells per face side (a multiple of COARSE)
+};
+
+// Table geometry for G cells per side from the per-face bounding rectangles (in probe cells) of the occupied probe
+// cells: probe rect -> coarse cells (conservative, +1 probe cell of slack) -> fine cells.  Returns the number of
+// fine cells.
+__device__ inline int64_t plan_tables(int G, const int rect[24], FaceTable &fine, FaceTable &coarse, int64_t &n_coarse)
 {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int Gc = G / COARSE;
+    int64_t nf = 0, nc = 0;
+    for (int f = 0; f < 6; ++f) {
+        const int *r = rect + 4 * f;
+        fine.base[f] = nf;
+        coarse.base[f] = nc;
+        if (r[2] < r[0]) {
+            fine.fu0[f] = fine.fv0[f] = fine.fw[f] = fine.fh[f] = 0;
+            coarse.fu0[f] = coarse.fv0[f] = coarse.fw[f] = coarse.fh[f] = 0;
+            continue;
+        }
+        // [cu0, cu1) coarse cells
+        int cu0 = max(0, (int)floor((double)(r[0] - 1) * Gc / OCC_G)), cv0 = max(0, (int)floor((double)(r[1] - 1) * Gc / OCC_G));
+        int cu1 = min(Gc, (int)ceil((double)(r[2] + 2) * Gc / OCC_G)), cv1 = min(Gc, (int)ceil((double)(r[3] + 2) * Gc / OCC_G));
+        if (cu1 <= cu0) cu1 = cu0 + 1;
+        if (cv1 <= cv0) cv1 = cv0 + 1;
+        coarse.fu0[f] = cu0;
+        coarse.fv0[f] = cv0;
+        coarse.fw[f] = cu1 - cu0;
+        coarse.fh[f] = cv1 - cv0;
+        fine.fu0[f] = cu0 * COARSE;
+        fine.fv0[f] = cv0 * COARSE;
+        fine.fw[f] = (cu1 - cu0) * COARSE;
+        fine.fh[f] = (cv1 - cv0) * COARSE;
+        nc += (int64_t)coarse.fw[f] * coarse.fh[f];
+        nf += (int64_t)fine.fw[f] * fine.fh[f];
+    }
+    n_coarse = nc;
+    return nf;
+}
+
+// The plan (one block): totals of pass 1, bounding rectangles of the occupancy probe, then the cell size - a cell
+// should hold ~lambda points, so that the 3x3 block a query scans first holds the k nearest with room to spare -
+// and the table geometry.  What index_build used to do on the host after a read-back.
+static __global__ void __launch_bounds__(1024)
+    build_plan_kernel(const uint8_t *__restrict__ occ, const uint2 *__restrict__ block_counts,
+                      const BuildCounters *__restrict__ counters, const PlanParams pp, IndexMeta *__restrict__ meta)
+{
+    __shared__ unsigned s_nv, s_ns, s_no;
+    __shared__ int s_rect[24];
+    const int tid = threadIdx.x;
+    if (tid == 0) s_nv = s_ns = s_no = 0;
+    if (tid < 24) s_rect[tid] = (tid & 3) < 2 ? (1 << 30) : -1;
+    __syncthreads();
     unsigned nv = 0, ns = 0, no = 0;
-    for (int64_t b = tid; b < n_blocks; b += nth) {
-        uint2 c = block_counts[b];
+    for (int64_t b = tid; b < pp.n_blocks; b += blockDim.x) {
+        const uint2 c = block_counts[b];
         nv += c.x;
         ns += c.y;
     }
     // four probe cells per thread (one 32-bit load); a warp covers one row of OCC_G = 128 cells of one face, so
-    // its bounding box is reduced in registers and costs at most four atomics
+    // its bounding box is reduced in registers and costs at most four shared-memory atomics
     static_assert(OCC_G == 128, "a warp reads exactly one row of probe cells");
     const uint32_t *occ4 = reinterpret_cast<const uint32_t *>(occ);
-    for (int w = tid; w < 6 * OCC_G * OCC_G / 4; w += nth) {
+    for (int w = tid; w < 6 * OCC_G * OCC_G / 4; w += blockDim.x) {
         const uint32_t bits = occ4[w];
         const int i = w * 4, f = i / (OCC_G * OCC_G), iv = (i / OCC_G) % OCC_G, iu = i % OCC_G;
         int u0 = 1 << 30, u1 = -1;
@@ -497,11 +530,11 @@ static __global__ void build_reduce_kernel(const uint8_t *__restrict__ occ, cons
             u0 = min(u0, __shfl_xor_sync(0xffffffffu, u0, o));
             u1 = max(u1, __shfl_xor_sync(0xffffffffu, u1, o));
         }
-        if ((threadIdx.x & 31) == 0 && u1 >= 0) {
-            atomicMin(&rect[4 * f + 0], u0);
-            atomicMin(&rect[4 * f + 1], iv);
-            atomicMax(&rect[4 * f + 2], u1);
-            atomicMax(&rect[4 * f + 3], iv);
+        if ((tid & 31) == 0 && u1 >= 0) {
+            atomicMin(&s_rect[4 * f + 0], u0);
+            atomicMin(&s_rect[4 * f + 1], iv);
+            atomicMax(&s_rect[4 * f + 2], u1);
+            atomicMax(&s_rect[4 * f + 3], iv);
         }
     }
 #pragma unroll
@@ -510,11 +543,68 @@ static __global__ void build_reduce_kernel(const uint8_t *__restrict__ occ, cons
         ns += __shfl_xor_sync(0xffffffffu, ns, o);
         no += __shfl_xor_sync(0xffffffffu, no, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (nv) atomicAdd(&counters->n_valid, nv);
-        if (ns) atomicAdd(&counters->n_skipped, ns);
-        if (no) atomicAdd(&counters->n_occ, no);
+    if ((tid & 31) == 0) {
+        if (nv) atomicAdd(&s_nv, nv);
+        if (ns) atomicAdd(&s_ns, ns);
+        if (no) atomicAdd(&s_no, no);
     }
+    __syncthreads();
+    if (tid != 0) return;
+    IndexMeta m;
+    m.n_valid = s_nv;
+    m.n_skipped = s_ns;
+    m.first_valid_source = counters->first_inv ? ~counters->first_inv : 0u;
+    m.n_occ = s_no;
+    m.all_valid = (int64_t)s_nv == pp.n;
+    m.status = 0;
+    m.n_source = pp.n;
+    m.n_indexed = (int64_t)s_nv - (int64_t)s_ns;
+    int rect[24];
+    for (int i = 0; i < 24; ++i) rect[i] = s_rect[i];
+    if (m.n_indexed <= 0) {
+        m.n_indexed = 0;
+        for (int i = 0; i < 24; ++i) rect[i] = (i & 3) < 2 ? 1 : 0;  // every face empty
+    }
+    const double n_occ = s_no ? (double)s_no : 1.0;
+    const double g = (double)OCC_G * sqrt((double)m.n_indexed / (n_occ * pp.lambda));
+    int G = (int)ceil(g / COARSE) * COARSE;
+    if (G < COARSE) G = COARSE;
+    if (G > pp.g_max) G = pp.g_max;
+    int64_t nc = 0;
+    int64_t nf = plan_tables(G, rect, m.fine, m.coarse, nc);
+    // a source made of clusters far apart on one face spans a rectangle that is mostly empty: coarsen the grid
+    // until the table fits its allocation (4 entries per source point)
+    while (nf > pp.cap_cells && G > COARSE) {
+        G = max(COARSE, (G / 2 / COARSE) * COARSE);
+        nf = plan_tables(G, rect, m.fine, m.coarse, nc);
+    }
+    if (nf > pp.cap_cells) {  // cannot happen for cap_cells >= 6 * COARSE^2: reported when the host asks
+        m.status = 1;
+        m.n_indexed = 0;
+        for (int i = 0; i < 24; ++i) rect[i] = (i & 3) < 2 ? 1 : 0;
+        nf = plan_tables(G, rect, m.fine, m.coarse, nc);
+    }
+    m.G = G;
+    m.Gc = G / COARSE;
+    m.n_cells = nf;
+    m.n_coarse = nc;
+    *meta = m;
+}
+
+// zero table[0 .. n_cells + 4) and coarse[0 .. n_coarse + 4): the sizes are only known on the device
+static __global__ void build_clear_kernel(const IndexMeta *__restrict__ meta, uint32_t *__restrict__ cell_alloc,
+                                          uint32_t *__restrict__ coarse_alloc)
+{
+    const int64_t nf = meta->n_cells + 4, nc = meta->n_coarse + 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    // cell_alloc is 16-byte aligned: whole uint4 stores, the tail word by word
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < nf; i += stride) {
+        if (i + 4 <= nf)
+            *reinterpret_cast<uint4 *>(cell_alloc + i) = make_uint4(0, 0, 0, 0);
+        else
+            for (int64_t j = i; j < nf; ++j) cell_alloc[j] = 0;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += stride / 4) coarse_alloc[i] = 0;
 }
 
 __device__ __forceinline__ int64_t table_key(const FaceTable &t, int face, int iu, int iv)
@@ -522,18 +612,39 @@ __device__ __forceinline__ int64_t table_key(const FaceTable &t, int face, int i
     return t.base[face] + (int64_t)(iv - t.fv0[face]) * t.fw[face] + (iu - t.fu0[face]);
 }
 
+// ECEF of one source point in the tree dtype T from lon/lat of dtype Tin.  Tin == T: the reference's chain in that
+// dtype.  float32 lon/lat into a float64 tree (XArrayResamplerNN, kd_tree.py:970-981): the reference transforms in
+// float32 (lonlat2xyz on float32 arrays) and only then widens (`astype(np.float64)`) - so does this.
+template <typename Tin, typename T>
+__device__ __forceinline__ void source_xyz(Tin lo, Tin la, T &x, T &y, T &z)
+{
+    Tin xi, yi, zi;
+    lonlat_to_xyz(lo, la, xi, yi, zi);
+    x = (T)xi, y = (T)yi, z = (T)zi;
+}
+
 // Pass 2: exact ECEF coordinates of the kept points, their cell key and the histogram into table[key + 1].
 // tmp[i] = (x, y, z, cell key) - the record's source index is its position i, so the fourth word carries the key
-// to pass 3.
-// SPARSE (a rank of a sharded run keeps a fraction of the points): the coordinates are only loaded for kept points;
-// otherwise all loads are issued up front.
-template <typename T, bool SPARSE>
+// to pass 3.  A rank of a sharded run keeps a fraction of the points ("sparse"): the coordinates are then only
+// loaded for kept points and tmp is only written for them; otherwise all loads are issued up front.
+template <typename Tin, typename T>
 __global__ void __launch_bounds__(BUILD_TPB)
-    build_xyz_kernel(const T *__restrict__ lon, const T *__restrict__ lat, int64_t n, const uint8_t *__restrict__ keep,
-                     int G, const FaceTable ft, Rec<T> *__restrict__ tmp, uint32_t *__restrict__ table)
+    build_xyz_kernel(const Tin *__restrict__ lon, const Tin *__restrict__ lat, int64_t n,
+                     const uint8_t *__restrict__ keep, const IndexMeta *__restrict__ meta, Rec<T> *__restrict__ tmp,
+                     uint32_t *__restrict__ table)
 {
+    __shared__ FaceTable ft;
+    __shared__ int s_G, s_sparse;
+    if (threadIdx.x == 0) {
+        ft = meta->fine;
+        s_G = meta->G;
+        s_sparse = meta->n_indexed * 2 < n;
+    }
+    __syncthreads();
+    const int G = s_G;
+    const bool sparse = s_sparse != 0;
     const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * BUILD_ITEMS) + threadIdx.x;
-    T lo[BUILD_ITEMS], la[BUILD_ITEMS];
+    Tin lo[BUILD_ITEMS], la[BUILD_ITEMS];
     uint8_t kp[BUILD_ITEMS];
 #pragma unroll
     for (int j = 0; j < BUILD_ITEMS; ++j) {
@@ -544,7 +655,7 @@ __global__ void __launch_bounds__(BUILD_TPB)
     for (int j = 0; j < BUILD_ITEMS; ++j) {
         const int64_t i = base + (int64_t)j * BUILD_TPB;
         lo[j] = la[j] = 0;
-        if (i < n && (!SPARSE || kp[j])) {
+        if (i < n && (!sparse || kp[j])) {
             lo[j] = lon[i];
             la[j] = lat[i];
         }
@@ -554,11 +665,11 @@ __global__ void __launch_bounds__(BUILD_TPB)
         const int64_t i = base + (int64_t)j * BUILD_TPB;
         if (!kp[j]) {
             // dense builds mark the few skipped points in tmp, so that pass 3 needs nothing but tmp
-            if (!SPARSE && i < n) store_rec(tmp + i, (T)0, (T)0, (T)0, CELL_SKIP);
+            if (!sparse && i < n) store_rec(tmp + i, (T)0, (T)0, (T)0, CELL_SKIP);
             continue;
         }
         T x, y, z;
-        lonlat_to_xyz(lo[j], la[j], x, y, z);
+        source_xyz<Tin, T>(lo[j], la[j], x, y, z);
         float fx, fy, fz;
         unit_f32<T>(x, y, z, fx, fy, fz);
         int face, iu, iv;
@@ -598,11 +709,12 @@ __global__ void __launch_bounds__(BUILD_TPB)
 
 // Pass 3: scatter.  table[c + 1] holds start(c) after the exclusive scan and ends as start(c + 1).
 constexpr int SCATTER_ITEMS = 4;
-template <typename T, bool SPARSE>
+template <typename T>
 __global__ void __launch_bounds__(BUILD_TPB)
     build_scatter_kernel(const Rec<T> *__restrict__ tmp, const uint8_t *__restrict__ keep, int64_t n,
-                         uint32_t *__restrict__ table, Rec<T> *__restrict__ recs)
+                         const IndexMeta *__restrict__ meta, uint32_t *__restrict__ table, Rec<T> *__restrict__ recs)
 {
+    const bool sparse = meta->n_indexed * 2 < n;  // uniform over the grid
     const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * SCATTER_ITEMS) + threadIdx.x;
     Rec<T> r[SCATTER_ITEMS];
     uint8_t kp[SCATTER_ITEMS];
@@ -614,13 +726,13 @@ __global__ void __launch_bounds__(BUILD_TPB)
         r[j].idx = CELL_SKIP;
         kp[j] = 0;
         if (i < n) {
-            if (SPARSE)
+            if (sparse)
                 kp[j] = keep[i];
             else
                 r[j] = load_rec(tmp + i);
         }
     }
-    if (SPARSE) {
+    if (sparse) {
 #pragma unroll
         for (int j = 0; j < SCATTER_ITEMS; ++j)
             if (kp[j]) r[j] = load_rec(tmp + base + (int64_t)j * BUILD_TPB);
@@ -645,28 +757,36 @@ __global__ void __launch_bounds__(BUILD_TPB)
 }
 
 // Coarse table: number of points in each COARSE x COARSE block of fine cells, from the fine row prefix sums.
-static __global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_start, const FaceTable fine,
-                                           const FaceTable coarse, int64_t n_coarse, uint32_t *__restrict__ ctable)
+static __global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_start, const IndexMeta *__restrict__ meta,
+                                           uint32_t *__restrict__ ctable)
 {
-    int64_t cc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cc >= n_coarse) return;
-    int face = 5;
+    const FaceTable &fine = meta->fine, &coarse = meta->coarse;
+    const int64_t n_coarse = meta->n_coarse;
+    for (int64_t cc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cc < n_coarse; cc += (int64_t)gridDim.x * blockDim.x) {
+        int face = 5;
 #pragma unroll
-    for (int f = 4; f >= 0; --f)
-        if (cc < coarse.base[f + 1]) face = f;
-    int64_t local = cc - coarse.base[face];
-    int cu = coarse.fu0[face] + (int)(local % coarse.fw[face]);
-    int cv = coarse.fv0[face] + (int)(local / coarse.fw[face]);
-    uint32_t tot = 0;
-    for (int r = 0; r < COARSE; ++r) {
-        int64_t k0 = table_key(fine, face, cu * COARSE, cv * COARSE + r);
-        tot += cell_start[k0 + COARSE] - cell_start[k0];
+        for (int f = 4; f >= 0; --f)
+            if (cc < coarse.base[f + 1]) face = f;
+        int64_t local = cc - coarse.base[face];
+        int cu = coarse.fu0[face] + (int)(local % coarse.fw[face]);
+        int cv = coarse.fv0[face] + (int)(local / coarse.fw[face]);
+        uint32_t tot = 0;
+        for (int r = 0; r < COARSE; ++r) {
+            int64_t k0 = table_key(fine, face, cu * COARSE, cv * COARSE + r);
+            tot += cell_start[k0 + COARSE] - cell_start[k0];
+        }
+        ctable[cc + 1] = tot;
     }
-    ctable[cc + 1] = tot;
 }
 
-template <typename T>
-int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const prs_reduce_box *box,
+inline int64_t index_cap_cells(int64_t n) { return 4 * n + 65536; }
+
+// Queue the whole build on `st`.  Nothing here waits for the device: the cell size and the table geometry are
+// decided by build_plan_kernel and stay in device memory (IndexMeta); the arrays are allocated for the largest
+// size they can take (records: one per source point; cell table: 4 entries per source point, the plan coarsens
+// the grid to fit), so their sizes - and the stream-ordered pool's reuse of them - do not depend on the data.
+template <typename Tin, typename T>
+int index_build_t(const Tin *lon, const Tin *lat, int64_t n, uint8_t *valid, const prs_reduce_box *box,
                   const uint8_t *premask, const uint8_t *exclude, const uint8_t *cover, int flags, int k_hint,
                   double radius_hint, prs_index *ix, cudaStream_t st)
 {
@@ -681,10 +801,10 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
     prs_reduce_box bx0;
     memset(&bx0, 0, sizeof(bx0));
     if (box) bx0 = *box;
-    BoxT<T> bx;
+    BoxT<Tin> bx;
     make_box(bx0, bx);
     const size_t occ_n = 6ull * OCC_G * OCC_G;
-    // workspace: counters | rect[24] | occ[occ_n] | block_counts[n_blocks] || unsorted records || keep flags
+    // workspace: counters | occ[occ_n] | block_counts[n_blocks] || unsorted records || keep flags
     const size_t off_counts = (256 + occ_n + 15) & ~(size_t)15;
     const size_t scratch_bytes = (off_counts + sizeof(uint2) * (size_t)n_blocks + 255) & ~(size_t)255;
     const size_t tmp_bytes = (sizeof(Rec<T>) * (size_t)n + 255) & ~(size_t)255;
@@ -695,146 +815,80 @@ int index_build_t(const T *lon, const T *lat, int64_t n, uint8_t *valid, const p
     uint8_t *scratch = (uint8_t *)ws_base;
     PRS_CK(cudaMemsetAsync(scratch, 0, off_counts, st));
     BuildCounters *counters = (BuildCounters *)scratch;
-    int *rect_dev = (int *)(scratch + 32);
     uint8_t *occ = scratch + 256;
     uint2 *block_counts = (uint2 *)(scratch + off_counts);
-    {
-        struct {
-            BuildCounters c;
-            uint32_t pad[4];
-            int rect[24];
-        } init;
-        memset(&init, 0, sizeof(init));
-        init.c.first_source = 0xFFFFFFFFu;
-        for (int f = 0; f < 6; ++f) {
-            init.rect[4 * f] = init.rect[4 * f + 1] = 1 << 30;
-            init.rect[4 * f + 2] = init.rect[4 * f + 3] = -1;
-        }
-        PRS_CK(cudaMemcpyAsync(scratch, &init, sizeof(init), cudaMemcpyHostToDevice, st));
-    }
-    // pass 1: validity, selection, occupancy probe (records are addressed by source index: no rank table needed)
     Rec<T> *tmp = (Rec<T> *)(scratch + scratch_bytes);
     uint8_t *keep = scratch + scratch_bytes + tmp_bytes;
-    build_select_kernel<T><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, valid, compute_valid, bx, premask, exclude,
-                                                                     cover, keep, occ, counters, block_counts);
-    PRS_CKL();
-    build_reduce_kernel<<<96, TPB, 0, st>>>(occ, block_counts, n_blocks, rect_dev, counters);
-    PRS_CKL();
-    timer.mark("pass 1 queued");
-    // the one host round trip of the build: sizes the cell grid
-    struct {
-        BuildCounters c;
-        uint32_t pad[4];
-        int rect[24];
-    } h;
-    rc = read_back_small(scratch, &h, sizeof(h), st);
-    if (rc != PRS_OK) return rc;
-    timer.mark("counters read back");
-    ix->n_valid = h.c.n_valid;
-    ix->n_indexed = (int64_t)h.c.n_valid - (int64_t)h.c.n_skipped;
-    ix->first_valid_source = h.c.first_source == 0xFFFFFFFFu ? 0u : h.c.first_source;
-    ix->all_valid = (int64_t)h.c.n_valid == n;
-    if ((flags & PRS_BUILD_RANKS) && !ix->all_valid && ix->n_valid > 0) {
-        // rank of every source point among the valid ones = the index space of index_array (kd_tree.py:635)
+    // long-lived arrays, sized for the worst case
+    ix->cap_cells = index_cap_cells(n);
+    ix->cap_coarse = ix->cap_cells / (COARSE * COARSE) + 8;
+    PRS_CK(cudaMallocAsync((void **)&ix->meta_dev, sizeof(IndexMeta), st));
+    PRS_CK(cudaMallocAsync((void **)&ix->cell_alloc, sizeof(uint32_t) * (size_t)(ix->cap_cells + 8), st));
+    PRS_CK(cudaMallocAsync((void **)&ix->coarse_alloc, sizeof(uint32_t) * (size_t)(ix->cap_coarse + 8), st));
+    PRS_CK(cudaMallocAsync((void **)&ix->recs, sizeof(Rec<T>) * (size_t)n, st));
+    // three leading pad words: cell_start + 1 (the array the scan walks) is then 16-byte aligned for 128-bit accesses
+    ix->cell_start = ix->cell_alloc + 3;
+    ix->coarse_start = ix->coarse_alloc + 3;
+    ix->bytes = sizeof(IndexMeta) + sizeof(uint32_t) * (size_t)(ix->cap_cells + ix->cap_coarse + 16) + sizeof(Rec<T>) * (size_t)n;
+    if (flags & PRS_BUILD_RANKS) {
         PRS_CK(cudaMallocAsync((void **)&ix->rank, sizeof(uint32_t) * (size_t)n, st));
         ix->bytes += sizeof(uint32_t) * (size_t)n;
+    }
+    timer.mark("allocated");
+    // pass 1: validity, selection, occupancy probe (records are addressed by source index: no rank table needed)
+    build_select_kernel<Tin><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, valid, compute_valid, bx, premask, exclude,
+                                                                       cover, keep, occ, counters, block_counts);
+    PRS_CKL();
+    // the plan: cell size and table geometry, on the device
+    PlanParams pp;
+    pp.n = n;
+    pp.n_blocks = n_blocks;
+    pp.cap_cells = ix->cap_cells;
+    // target points per cell: the hot path of the query scans the 3x3 block around a point's cell (9*lambda
+    // candidates) and that block should hold the k nearest with room to spare
+    pp.lambda = k_hint > 4 ? 0.5 * (double)k_hint : 2.0;
+    if (const char *env = getenv("PRS_CELL_OCCUPANCY")) {
+        double v = atof(env);
+        if (v > 0) pp.lambda = v;
+    }
+    pp.g_max = 16384;
+    if (const char *env = getenv("PRS_MAX_CELLS_PER_SIDE")) {
+        int v = atoi(env);
+        if (v >= COARSE) pp.g_max = (v / COARSE) * COARSE;
+    }
+    build_plan_kernel<<<1, 1024, 0, st>>>(occ, block_counts, counters, pp, ix->meta_dev);
+    PRS_CKL();
+    PRS_CK(cudaEventRecord(ix->planned, st));
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        PRS_CK(cudaGetDevice(&dev));
+        PRS_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    build_clear_kernel<<<n_sm * 8, TPB, 0, st>>>(ix->meta_dev, ix->cell_alloc, ix->coarse_alloc);
+    PRS_CKL();
+    if (ix->rank) {
+        // rank of every source point among the valid ones = the index space of index_array (kd_tree.py:635)
         rc = scan_u32<uint8_t>(valid, ix->rank, n, 0, nullptr, st);
         if (rc != PRS_OK) return rc;
     }
-    if (ix->n_indexed <= 0) {
-        ix->n_indexed = 0;
-        ix->G = COARSE;
-        ix->Gc = 1;
-        return PRS_OK;
-    }
-    // target points per cell: the hot path of the query scans the 3x3 block around a point's cell (9*lambda
-    // candidates) and that block should hold the k nearest with room to spare
-    double lambda = k_hint > 4 ? 0.5 * (double)k_hint : 2.0;
-    if (const char *env = getenv("PRS_CELL_OCCUPANCY")) {
-        double v = atof(env);
-        if (v > 0) lambda = v;
-    }
-    uint32_t n_occ = h.c.n_occ ? h.c.n_occ : 1;
-    double g = (double)OCC_G * sqrt((double)ix->n_indexed / ((double)n_occ * lambda));
-    int G = (int)ceil(g / COARSE) * COARSE;
-    int Gmax = 16384;
-    if (const char *env = getenv("PRS_MAX_CELLS_PER_SIDE")) {
-        int v = atoi(env);
-        if (v >= COARSE) Gmax = (v / COARSE) * COARSE;
-    }
-    if (G < COARSE) G = COARSE;
-    if (G > Gmax) G = Gmax;
-    ix->G = G;
-    ix->Gc = G / COARSE;
-    // table rectangles: probe rect -> coarse cells (conservative, +1 probe cell of slack) -> fine cells
-    int64_t nf = 0, nc = 0;
-    for (int f = 0; f < 6; ++f) {
-        const int *r = h.rect + 4 * f;
-        ix->fine.base[f] = nf;
-        ix->coarse.base[f] = nc;
-        if (r[2] < r[0]) {
-            ix->fine.fu0[f] = ix->fine.fv0[f] = ix->fine.fw[f] = ix->fine.fh[f] = 0;
-            ix->coarse.fu0[f] = ix->coarse.fv0[f] = ix->coarse.fw[f] = ix->coarse.fh[f] = 0;
-            continue;
-        }
-        auto lo = [&](int p) { long v = (long)floor((double)(p - 1) * ix->Gc / OCC_G); return (int)(v < 0 ? 0 : v); };
-        auto hi = [&](int p) {
-            long v = (long)ceil((double)(p + 2) * ix->Gc / OCC_G);
-            return (int)(v > ix->Gc ? ix->Gc : v);
-        };
-        int cu0 = lo(r[0]), cv0 = lo(r[1]), cu1 = hi(r[2]), cv1 = hi(r[3]);  // [cu0, cu1) coarse cells
-        if (cu1 <= cu0) cu1 = cu0 + 1;
-        if (cv1 <= cv0) cv1 = cv0 + 1;
-        ix->coarse.fu0[f] = cu0;
-        ix->coarse.fv0[f] = cv0;
-        ix->coarse.fw[f] = cu1 - cu0;
-        ix->coarse.fh[f] = cv1 - cv0;
-        ix->fine.fu0[f] = cu0 * COARSE;
-        ix->fine.fv0[f] = cv0 * COARSE;
-        ix->fine.fw[f] = (cu1 - cu0) * COARSE;
-        ix->fine.fh[f] = (cv1 - cv0) * COARSE;
-        nc += (int64_t)ix->coarse.fw[f] * ix->coarse.fh[f];
-        nf += (int64_t)ix->fine.fw[f] * ix->fine.fh[f];
-    }
-    ix->n_cells = nf;
-    ix->n_coarse = nc;
-    if (nf >= 0xFFFFFFF0LL) return fail(PRS_ENOSUP, "cell table too large");
     // pass 2 + scan + pass 3
-    // three leading pad words: cell_start + 1 (the array the scan walks) is then 16-byte aligned for 128-bit accesses
-    PRS_CK(cudaMallocAsync((void **)&ix->cell_alloc, sizeof(uint32_t) * (size_t)(nf + 4), st));
-    ix->cell_start = ix->cell_alloc + 3;
-    ix->bytes += sizeof(uint32_t) * (size_t)(nf + 4);
-    PRS_CK(cudaMemsetAsync(ix->cell_alloc, 0, sizeof(uint32_t) * (size_t)(nf + 4), st));
-    timer.mark("cell table allocated");
-    if (ix->n_indexed * 2 < n)  // a sharded rank (or a heavily masked source): most points are skipped
-        build_xyz_kernel<T, true><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, G, ix->fine, tmp, ix->cell_start);
-    else
-        build_xyz_kernel<T, false><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, G, ix->fine, tmp, ix->cell_start);
+    build_xyz_kernel<Tin, T><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, ix->meta_dev, tmp, ix->cell_start);
     PRS_CKL();
-    rc = scan_u32<uint32_t>(ix->cell_start + 1, ix->cell_start + 1, nf, 0, nullptr, st);
+    rc = scan_u32_dev(ix->cell_start + 1, ix->cap_cells, &ix->meta_dev->n_cells, 0, st);
     if (rc != PRS_OK) return rc;
-    size_t rec_bytes = sizeof(Rec<T>) * (size_t)ix->n_indexed;
-    PRS_CK(cudaMallocAsync((void **)&ix->recs, rec_bytes, st));
-    timer.mark("records allocated");
-    ix->bytes += rec_bytes;
     const unsigned scatter_blocks = (unsigned)((n + BUILD_TPB * SCATTER_ITEMS - 1) / (BUILD_TPB * SCATTER_ITEMS));
-    if (ix->n_indexed * 2 < n)
-        build_scatter_kernel<T, true><<<scatter_blocks, BUILD_TPB, 0, st>>>(tmp, keep, n, ix->cell_start, (Rec<T> *)ix->recs);
-    else
-        build_scatter_kernel<T, false><<<scatter_blocks, BUILD_TPB, 0, st>>>(tmp, keep, n, ix->cell_start, (Rec<T> *)ix->recs);
+    build_scatter_kernel<T><<<scatter_blocks, BUILD_TPB, 0, st>>>(tmp, keep, n, ix->meta_dev, ix->cell_start, (Rec<T> *)ix->recs);
     PRS_CKL();
     // coarse table
-    PRS_CK(cudaMallocAsync((void **)&ix->coarse_alloc, sizeof(uint32_t) * (size_t)(nc + 4), st));
-    ix->coarse_start = ix->coarse_alloc + 3;
-    ix->bytes += sizeof(uint32_t) * (size_t)(nc + 4);
-    PRS_CK(cudaMemsetAsync(ix->coarse_start, 0, sizeof(uint32_t), st));
-    build_coarse_kernel<<<(unsigned)((nc + TPB - 1) / TPB), TPB, 0, st>>>(ix->cell_start, ix->fine, ix->coarse, nc,
-                                                                         ix->coarse_start);
+    build_coarse_kernel<<<n_sm * 4, TPB, 0, st>>>(ix->cell_start, ix->meta_dev, ix->coarse_start);
     PRS_CKL();
-    rc = scan_u32<uint32_t>(ix->coarse_start + 1, ix->coarse_start + 1, nc, 1, nullptr, st);
+    rc = scan_u32_dev(ix->coarse_start + 1, ix->cap_coarse, &ix->meta_dev->n_coarse, 1, st);
     if (rc != PRS_OK) return rc;
     timer.mark("all queued");
     return PRS_OK;
 }
+
+#endif  // PRS_WITH_INDEX_BUILD
 
 }  // namespace prs

@@ -14,7 +14,7 @@ inline int64_t tile_count(const QueryParams &P)
 
 // Classification + fill of the dead tiles (classify_kernel); live[] / n_live receive the tiles left to search.
 template <typename T, int TK>
-int launch_classify_tk(const QueryParams &P, const IndexView<T> &ix, int64_t tiles, uint32_t *live, uint32_t *n_live,
+int launch_classify_tk(const QueryParams &P, const IndexRef<T> &ix, int64_t tiles, uint32_t *live, uint32_t *n_live,
                        cudaStream_t st)
 {
     PRS_CK(cudaMemsetAsync(n_live, 0, sizeof(uint32_t), st));
@@ -23,7 +23,7 @@ int launch_classify_tk(const QueryParams &P, const IndexView<T> &ix, int64_t til
     return PRS_OK;
 }
 template <typename T>
-int launch_classify(const QueryParams &P, const IndexView<T> &ix, int64_t tiles, uint32_t *live, uint32_t *n_live,
+int launch_classify(const QueryParams &P, const IndexRef<T> &ix, int64_t tiles, uint32_t *live, uint32_t *n_live,
                     cudaStream_t st)
 {
     switch (P.tk) {
@@ -39,7 +39,7 @@ int launch_classify(const QueryParams &P, const IndexView<T> &ix, int64_t tiles,
 // Search of the live tiles (query_kernel): persistent-style grid, a multiple of the SM count, blocks stride over
 // the live list.  Dynamic shared memory: the record staging buffer (+ the row stage of the nearest epilogue).
 template <typename T, int K, int EPI>
-int launch_search(const QueryParams &P, const IndexView<T> &ix, int64_t tiles, const uint32_t *live,
+int launch_search(const QueryParams &P, const IndexRef<T> &ix, int64_t tiles, const uint32_t *live,
                   const uint32_t *n_live, cudaStream_t st)
 {
     int dev = 0;
@@ -47,7 +47,9 @@ int launch_search(const QueryParams &P, const IndexView<T> &ix, int64_t tiles, c
     static int n_sm[64] = {0};
     static bool configured[64] = {false};
     const int slot = dev < 0 || dev >= 64 ? 0 : dev;
-    const size_t smem = PRS_STAGE_BYTES(K) + (EPI == PRS_EPI_NEAREST ? QROWS * 32 * STAGE_ROW_BYTES : 0);
+    // k >= 4: staged records + cell-table stretch; nearest (k = 1, never staged): the row stage of its epilogue
+    const size_t smem = K >= 4 ? PRS_STAGE_BYTES(K) + STAGE_CELLS * sizeof(uint32_t)
+                               : (EPI == PRS_EPI_NEAREST ? QROWS * 32 * STAGE_ROW_BYTES : 0);
     if (!configured[slot] || slot != dev) {
         PRS_CK(cudaDeviceGetAttribute(&n_sm[slot], cudaDevAttrMultiProcessorCount, dev));
         PRS_CK(cudaFuncSetAttribute(query_kernel<T, K, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -15,6 +15,7 @@
 #include "prs_common.cuh"
 #include "prs_index.cuh"
 #include "prs_proj.cuh"
+#include <type_traits>
 
 namespace prs {
 
@@ -108,16 +109,36 @@ template <typename T, int K> struct TopK {
     __device__ __forceinline__ bool full() const { return id[K - 1] != PRS_NONE; }
 };
 
-template <typename T> struct IndexView {
+// What the kernels know about the index: the device-resident description (IndexMeta, copied into shared memory by
+// every block - the host never needs to have seen it) plus the arrays.
+template <typename T> struct IndexView : IndexMeta {
     const Rec<T> *recs;
     const uint32_t *cell_start;
     const uint32_t *coarse_start;
-    const uint32_t *rank;  // NULL when rank == source index
-    FaceTable fine, coarse;
-    int G, Gc;
-    uint32_t n_valid;
-    uint32_t first_valid_source;
+    const uint32_t *rank;  // NULL when the index was built without PRS_BUILD_RANKS
 };
+template <typename T> struct IndexRef {  // kernel parameter
+    const Rec<T> *recs;
+    const uint32_t *cell_start;
+    const uint32_t *coarse_start;
+    const uint32_t *rank;
+    const IndexMeta *meta;
+};
+// All threads of the block call this (it ends with a barrier).
+template <typename T> __device__ __forceinline__ void load_index_view(IndexView<T> &ix, const IndexRef<T> &ref)
+{
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(ref.meta);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(static_cast<IndexMeta *>(&ix));
+    static_assert(sizeof(IndexMeta) % 4 == 0, "IndexMeta is copied word by word");
+    for (int i = threadIdx.x; i < (int)(sizeof(IndexMeta) / 4); i += blockDim.x) dst[i] = __ldg(src + i);
+    if (threadIdx.x == 0) {
+        ix.recs = ref.recs;
+        ix.cell_start = ref.cell_start;
+        ix.coarse_start = ref.coarse_start;
+        ix.rank = ref.rank;
+    }
+    __syncthreads();
+}
 
 struct CellRect {
     int u0, u1, v0, v1;
@@ -262,10 +283,13 @@ __device__ __forceinline__ void scan_rect(const IndexView<T> &ix, int face, cons
             }
             if (a > b) continue;
             const uint32_t s = __ldg(row + a), e = __ldg(row + b + 1);
+            // two records in flight per step (one load per iteration leaves the thread waiting a full memory round
+            // trip per candidate)
 #pragma unroll 1
-            for (uint32_t i = s; i < e; ++i) {
-                Rec<T> r = load_rec(ix.recs + i);
-                top.offer(dist2<T>(qx, qy, qz, r.x, r.y, r.z), r.idx, dub);
+            for (uint32_t i = s; i < e; i += 2) {
+                const Rec<T> r0 = load_rec(ix.recs + i), r1 = load_rec(ix.recs + min(i + 1, e - 1));
+                top.offer(dist2<T>(qx, qy, qz, r0.x, r0.y, r0.z), r0.idx, dub);
+                if (i + 1 < e) top.offer(dist2<T>(qx, qy, qz, r1.x, r1.y, r1.z), r1.idx, dub);
             }
         }
     }
@@ -397,30 +421,34 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // Candidate records of one tile, staged in shared memory.  The threads of a tile (32 x QROWS neighbouring target
 // points) scan almost the same cells, and one row of cells is ONE contiguous run of records: the block takes, for
 // every row of cells any of its points touches, the span of cells between the leftmost and the rightmost touched
-// one (the "hull" of the tile's 3x3 blocks - tight also when the tile lies diagonally on the cube face) and fetches
-// each row's run with one bulk copy.
+// one (the "hull" of the tile's home blocks - tight also when the tile lies diagonally on the cube face) and fetches
+// each row's run with one bulk copy.  The matching stretch of the cell table is staged next to it, so that a thread
+// finds the bounds of its runs without going to global memory.
 constexpr int HULL_ROWS = 64;  // rows of cells a staged tile may span (rows are slotted modulo this)
-// Shared memory for staged records per block: a tile's hull holds roughly (points per cell) x (cells the tile
-// covers + a margin of one cell), and cells are sized for ~max(2, k / 2) points - narrow lists need less.
+constexpr int HOME_MAX = 3;    // largest half-width of a home block: (2 * 3 + 1)^2 cells
+// Shared memory per block: records + cell-table stretch.  A tile's hull holds roughly (points per cell) x (cells the
+// tile covers + a margin of m cells), and cells are sized for ~max(2, k / 2) points.
 #ifndef PRS_STAGE_BYTES
-#define PRS_STAGE_BYTES(K) ((K) <= 1 ? 16384 : (K) <= 4 ? 32768 : 49152)
+#define PRS_STAGE_BYTES(K) ((K) <= 4 ? 24576 : 40960)
 #endif
+constexpr int STAGE_CELLS = 2048;  // entries of the staged cell-table stretch (8 KB)
 struct StageCtx {
     unsigned long long bar;          // mbarrier: 32 arrivals (warp 0) + the bytes of the row copies
     int umin[HULL_ROWS], umax[HULL_ROWS];
     uint32_t gstart[HULL_ROWS];      // index of the first staged record of the row in recs[]
-    uint32_t sbase[HULL_ROWS];       // ... and its slot in the staging buffer
+    uint32_t sbase[HULL_ROWS];       // ... and its slot in the record buffer
+    uint32_t csbase[HULL_ROWS];      // slot of cell_start[row][umin] in the staged cell-table stretch
     int vlo, vhi;
     unsigned faces;
     int staged;                      // 1: the tile's candidates are (being) staged
 };
 
-// Home cell of a query point and the (clipped) 3x3 block around it.
+// Home cell of a query point and the (clipped) block of (2m + 1)^2 cells around it.
 struct Home {
     int face, cu, cv;
     CellRect hb;  // empty (u0 > u1) when the block lies outside the table
 };
-template <typename T> __device__ __forceinline__ Home home_of(const IndexView<T> &ix, T qx, T qy, T qz)
+template <typename T> __device__ __forceinline__ Home home_cell(const IndexView<T> &ix, T qx, T qy, T qz)
 {
     const float invR = (float)(1.0 / PRS_R);
     const float fx = (float)qx * invR, fy = (float)qy * invR, fz = (float)qz * invR;
@@ -429,28 +457,52 @@ template <typename T> __device__ __forceinline__ Home home_of(const IndexView<T>
     face_uv(fx, fy, fz, h.face, hu, hv);
     h.cu = cell_coord(warp_uv(hu), ix.G);
     h.cv = cell_coord(warp_uv(hv), ix.G);
+    h.hb.u0 = h.hb.v0 = 1;
+    h.hb.u1 = h.hb.v1 = 0;
+    return h;
+}
+template <typename T> __device__ __forceinline__ void home_block(const IndexView<T> &ix, Home &h, int m)
+{
     const FaceTable &ft = ix.fine;
-    h.hb.u0 = max(h.cu - 1, ft.fu0[h.face]);
-    h.hb.u1 = min(h.cu + 1, ft.fu0[h.face] + ft.fw[h.face] - 1);
-    h.hb.v0 = max(h.cv - 1, ft.fv0[h.face]);
-    h.hb.v1 = min(h.cv + 1, ft.fv0[h.face] + ft.fh[h.face] - 1);
+    h.hb.u0 = max(h.cu - m, ft.fu0[h.face]);
+    h.hb.u1 = min(h.cu + m, ft.fu0[h.face] + ft.fw[h.face] - 1);
+    h.hb.v0 = max(h.cv - m, ft.fv0[h.face]);
+    h.hb.v1 = min(h.cv + m, ft.fv0[h.face] + ft.fh[h.face] - 1);
     if (ft.fw[h.face] == 0 || h.hb.u0 > h.hb.u1 || h.hb.v0 > h.hb.v1) {
         h.hb.u0 = h.hb.v0 = 1;
         h.hb.u1 = h.hb.v1 = 0;
     }
-    return h;
 }
 
-// Bounds [s, e) in recs[] of the (up to three) rows of the home block, the point's own row first: its candidates
-// are the likeliest neighbours, so the k-th distance tightens early and fewer later candidates enter the list.
+// Number of indexed points in the coarse cell (COARSE x COARSE fine cells) a home cell belongs to: the local density.
+template <typename T> __device__ __forceinline__ uint32_t home_density(const IndexView<T> &ix, const Home &h)
+{
+    const FaceTable &ct = ix.coarse;
+    const int cu = h.cu / COARSE, cv = h.cv / COARSE, f = h.face;
+    if (ct.fw[f] == 0 || cu < ct.fu0[f] || cu >= ct.fu0[f] + ct.fw[f] || cv < ct.fv0[f] || cv >= ct.fv0[f] + ct.fh[f]) return 0;
+    const uint32_t *p = ix.coarse_start + ct.base[f] + (int64_t)(cv - ct.fv0[f]) * ct.fw[f] + (cu - ct.fu0[f]);
+    return __ldg(p + 1) - __ldg(p);
+}
+
+// Half-width of the home block for k neighbours where a cell holds `lambda` points on average: the k-th neighbour
+// lies ~sqrt(k / (pi lambda)) cells away, and the block must contain the cap of that radius around a point that may
+// sit at the edge of its own cell.
+__device__ __forceinline__ int home_halfwidth(int k, float lambda)
+{
+    if (!(lambda > 0.f)) return HOME_MAX;
+    const float r = sqrtf((float)k / (3.14159265f * lambda));
+    return min(HOME_MAX, max(1, (int)ceilf(1.1f * r)));
+}
+
+// Bounds [s, e) in recs[] of the three rows of a 3x3 home block, the point's own row first: its candidates are the
+// likeliest neighbours, so the k-th distance tightens early and fewer later candidates enter the list.
 struct HomeRuns {
     uint32_t s[3], e[3];  // empty run (s == e) for a row outside the table
-    int v[3];
 };
 template <typename T> __device__ __forceinline__ HomeRuns home_runs(const IndexView<T> &ix, const Home &h)
 {
     HomeRuns r;
-    r.v[0] = h.cv, r.v[1] = h.cv - 1, r.v[2] = h.cv + 1;
+    const int v[3] = {h.cv, h.cv - 1, h.cv + 1};
     const FaceTable &ft = ix.fine;
     const int fw = ft.fw[h.face];
     const uint32_t *row0 = ix.cell_start + ft.base[h.face] - (int64_t)ft.fv0[h.face] * fw - ft.fu0[h.face];
@@ -458,8 +510,8 @@ template <typename T> __device__ __forceinline__ HomeRuns home_runs(const IndexV
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         r.s[j] = r.e[j] = 0;
-        if (h.hb.u0 <= h.hb.u1 && r.v[j] >= h.hb.v0 && r.v[j] <= h.hb.v1) {
-            const uint32_t *row = row0 + (int64_t)r.v[j] * fw;
+        if (h.hb.u0 <= h.hb.u1 && v[j] >= h.hb.v0 && v[j] <= h.hb.v1) {
+            const uint32_t *row = row0 + (int64_t)v[j] * fw;
             r.s[j] = __ldg(row + h.hb.u0);
             r.e[j] = __ldg(row + h.hb.u1 + 1);
         }
@@ -507,24 +559,29 @@ __device__ __forceinline__ Rec<double> lds_rec(const Rec<double> *p)
     return r;
 }
 
-// Hot path, records staged in shared memory (same order of candidates as scan_home_global).
+// Hot path, records and cell bounds staged in shared memory: the rows of the home block, the point's own row first,
+// then outwards.
 template <typename T, int K>
-__device__ __forceinline__ void scan_home_staged(const StageCtx &sc, const Rec<T> *srecs, const HomeRuns &hr, T qx, T qy,
-                                                 T qz, T dub, TopK<T, K> &top)
+__device__ __forceinline__ void scan_home_staged(const StageCtx &sc, const Rec<T> *srecs, const uint32_t *scs,
+                                                 const Home &h, T qx, T qy, T qz, T dub, TopK<T, K> &top)
 {
-    // slot of the first record of each run in the staging buffer
-    uint32_t b[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const int slot = hr.v[j] & (HULL_ROWS - 1);
-        b[j] = sc.sbase[slot] + (hr.s[j] - sc.gstart[slot]);
-    }
-    const uint32_t n0 = hr.e[0] - hr.s[0], n01 = n0 + (hr.e[1] - hr.s[1]), total = n01 + (hr.e[2] - hr.s[2]);
+    if (h.hb.u0 > h.hb.u1) return;  // home block outside the table
+    const int m = max(h.cv - h.hb.v0, h.hb.v1 - h.cv);
 #pragma unroll 1
-    for (uint32_t t = 0; t < total; ++t) {
-        const uint32_t i = t < n0 ? b[0] + t : (t < n01 ? b[1] + (t - n0) : b[2] + (t - n01));
-        const Rec<T> r = lds_rec(srecs + i);
-        top.template offer<false>(dist2<T>(qx, qy, qz, r.x, r.y, r.z), r.idx, dub);
+    for (int step = 0; step <= 2 * m; ++step) {
+        // step 0: cv; 1: cv - 1; 2: cv + 1; 3: cv - 2; ...
+        const int off = (step + 1) >> 1;
+        const int v = (step & 1) ? h.cv - off : h.cv + off;
+        if (v < h.hb.v0 || v > h.hb.v1) continue;
+        const int slot = v & (HULL_ROWS - 1);
+        const uint32_t *cs = scs + sc.csbase[slot] - sc.umin[slot];
+        const uint32_t s = cs[h.hb.u0], e = cs[h.hb.u1 + 1];
+        const Rec<T> *run = srecs + sc.sbase[slot] - sc.gstart[slot];
+#pragma unroll 1
+        for (uint32_t i = s; i < e; ++i) {
+            const Rec<T> r = lds_rec(run + i);
+            top.template offer<false>(dist2<T>(qx, qy, qz, r.x, r.y, r.z), r.idx, dub);
+        }
     }
 }
 
@@ -565,7 +622,10 @@ template <typename T> struct RowTab {  // per row: R*cos(lat), R*sin(lat)
 
 #define PRS_EPI_INFO 0
 #define PRS_EPI_NEAREST 1
-#define PRS_EPI_GAUSS 2
+#define PRS_EPI_GAUSS 2     // QueryParams::mode; the search kernels are instantiated per accumulation / data dtype:
+#define PRS_EPI_GAUSS_FF 2  //   float32 accumulation, float32 data (single channel, float32 tree)
+#define PRS_EPI_GAUSS_DF 3  //   float64 accumulation, float32 data
+#define PRS_EPI_GAUSS_DD 4  //   float64 accumulation, float64 data
 
 struct QueryParams {
     // target
@@ -669,8 +729,8 @@ __device__ __forceinline__ void load_channels(const Td *__restrict__ p, int nc, 
 // kd_tree.py:783).  Channels are processed four at a time so that a neighbour's row is read with 16-byte loads; per
 // channel the neighbours are accumulated in order i = 0..k-1 exactly like the reference's Python loop.
 template <typename T, typename Ta, typename Td, int K>
-__device__ __noinline__ void gauss_epilogue(const QueryParams &P, const IndexView<T> &ix, int64_t p,
-                                            const TopK<T, K> &top)
+__device__ __forceinline__ void gauss_epilogue(const QueryParams &P, const IndexView<T> &ix, int64_t p,
+                                               const TopK<T, K> &top)
 {
     const int C = P.channels, k = P.k;
     const bool want_uncert = P.stddev_out != nullptr;
@@ -1002,19 +1062,12 @@ __device__ __forceinline__ void emit_result(const QueryParams &P, const IndexVie
                 if (i == P.k - 1 && top.id[i] != PRS_NONE) kth = true;
             if (kth && P.flags[0] == 0) P.flags[0] = 1;
         }
-        if (!valid || top.id[0] == PRS_NONE) {
-            if (P.acc_f64)
-                gauss_empty<double>(P, p);
-            else
-                gauss_empty<float>(P, p);
-        } else if (P.acc_f64) {
-            if (P.data_f64)
-                gauss_epilogue<T, double, double, K>(P, ix, p, top);
-            else
-                gauss_epilogue<T, double, float, K>(P, ix, p, top);
-        } else {
-            gauss_epilogue<T, float, float, K>(P, ix, p, top);
-        }
+        typedef typename std::conditional<EPI == PRS_EPI_GAUSS_FF, float, double>::type Ta;
+        typedef typename std::conditional<EPI == PRS_EPI_GAUSS_DD, double, float>::type Td;
+        if (!valid || top.id[0] == PRS_NONE)
+            gauss_empty<Ta>(P, p);
+        else
+            gauss_epilogue<T, Ta, Td, K>(P, ix, p, top);
     }
 }
 
@@ -1128,7 +1181,7 @@ __device__ __forceinline__ bool tile_live(const QueryParams &P, const IndexView<
     tile_origin(P, TK, tile, lane, trow0, tcol);
     unsigned vmask;
     float cx, cy, cz, d2m;
-    bool is_live = tile_cap<T, TK>(P, tile, trow0, tcol, lane, vmask, cx, cy, cz, d2m) && ix.recs != nullptr;
+    bool is_live = tile_cap<T, TK>(P, tile, trow0, tcol, lane, vmask, cx, cy, cz, d2m) && ix.n_indexed > 0;
     if (is_live) {
         const T dub = (T)(P.radius * P.radius);
         const float sr = sqrtf(cap_s2<T>(dub));
@@ -1210,10 +1263,12 @@ __device__ __forceinline__ void tile_fill(const QueryParams &P, const IndexView<
 // Independent of the number of neighbours: a dead tile's result is sentinels / fill whatever k is.
 template <typename T, int TK>
 __global__ void __launch_bounds__(QWARPS * 32, 4)
-    classify_kernel(const __grid_constant__ QueryParams P, const __grid_constant__ IndexView<T> ix, uint32_t n_tiles,
+    classify_kernel(const __grid_constant__ QueryParams P, const __grid_constant__ IndexRef<T> ref, uint32_t n_tiles,
                     uint32_t *__restrict__ live, uint32_t *__restrict__ n_live)
 {
     __shared__ __align__(16) unsigned char stage_all[QWARPS][32 * STAGE_ROW_BYTES];
+    __shared__ IndexView<T> ix;
+    load_index_view<T>(ix, ref);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t tile = blockIdx.x * QWARPS + warp;
     if (tile >= n_tiles) return;
@@ -1230,33 +1285,41 @@ __global__ void __launch_bounds__(QWARPS * 32, 4)
 
 // ------------------------------------------------------------------------------------------ search
 // Kernel B: the tiles that may have neighbours.  One block of QROWS warps per live tile, one point per thread
-// (warp w takes row w of the tile).  Per tile:
-//   1. every thread finds its point's home cell; the block reduces, per row of cells, the span of cells its 3x3
-//      blocks touch (StageCtx::umin / umax);
-//   2. warp 0 reads the bounds of those spans from the cell table, lays the runs out back to back in the staging
-//      buffer and fetches each with one bulk copy (cp.async.bulk -> mbarrier); meanwhile every thread reads the bounds
-//      of its own three runs;
+// (warp w takes row w of the tile).
+//
+// k >= 4 (STAGED), per tile:
+//   1. every thread finds its point's home cell; every warp reads the local density of source points from the
+//      coarse table and picks the half-width m of its home blocks ((2m + 1)^2 cells that should hold the k nearest:
+//      cells are sized for the AVERAGE density, a swath is several times sparser at its edges than at nadir); the
+//      block reduces, per row of cells, the span of cells its home blocks touch (StageCtx::umin / umax);
+//   2. the rows are laid out back to back in the staging buffer and fetched with one bulk copy each (cp.async.bulk ->
+//      mbarrier, issued by warp 0); meanwhile all warps copy the matching stretch of the cell table;
 //   3. the threads scan their candidates from shared memory, prove the result with the closed-form cap bounds or
 //      continue in the general search (global memory), and write their result.
 // A tile whose points lie on different cube faces, span more than HULL_ROWS rows of cells or need more than the
-// staging buffer holds is searched straight from global memory (scan_home_global) - sparse targets like C2's
-// 5 km grid over a 1 km swath, where neighbouring points share no cells, always are.
+// staging buffers hold is searched straight from global memory (3x3 home blocks, scan_home_global).
+// k == 1: no staging (NOT STAGED) - a nearest-neighbour search reads a dozen candidates per point, and sparse targets
+// like C2's 5 km grid over a 1 km swath share no cells between neighbouring points.
 template <typename T, int K, int EPI>
 __global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS(K))
-    query_kernel(const __grid_constant__ QueryParams P, const __grid_constant__ IndexView<T> ix,
+    query_kernel(const __grid_constant__ QueryParams P, const __grid_constant__ IndexRef<T> ref,
                  const uint32_t *__restrict__ live, const uint32_t *__restrict__ n_live)
 {
-    extern __shared__ __align__(128) unsigned char dyn_smem[];  // staged records [+ row stage of the nearest epilogue]
+    constexpr bool STAGED = K >= 4;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];  // staged records, cell-table stretch [nearest: row stage]
     __shared__ StageCtx sc;
+    __shared__ IndexView<T> ix;
+    load_index_view<T>(ix, ref);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
     Rec<T> *srecs = reinterpret_cast<Rec<T> *>(dyn_smem);
-    unsigned char *stage = dyn_smem + PRS_STAGE_BYTES(K) + warp * (32 * STAGE_ROW_BYTES);  // EPI_NEAREST only
+    uint32_t *scs = reinterpret_cast<uint32_t *>(dyn_smem + PRS_STAGE_BYTES(K));
+    unsigned char *stage = dyn_smem + warp * (32 * STAGE_ROW_BYTES);  // EPI_NEAREST (never STAGED)
     constexpr uint32_t CAP = PRS_STAGE_BYTES(K) / sizeof(Rec<T>);
     const uint32_t count = __ldg(n_live);
     const T dub = (T)(P.radius * P.radius);  // pykdtree: dtype(distance_upper_bound ** 2)
     const float s2r = cap_s2<T>(dub), sr = sqrtf(s2r);
     const int TKr = P.tk;
-    if (tid == 0) mbar_init(reinterpret_cast<uint64_t *>(&sc.bar), 32);
+    if (STAGED && tid == 0) mbar_init(reinterpret_cast<uint64_t *>(&sc.bar), 32);
     uint32_t phase = 0;
 #pragma unroll 1
     for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) {
@@ -1271,9 +1334,28 @@ __global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS(K))
         Home h;
         h.face = 0, h.cu = h.cv = 0;
         h.hb.u0 = h.hb.v0 = 1, h.hb.u1 = h.hb.v1 = 0;
-        if (valid) h = home_of<T>(ix, qx, qy, qz);
+        if (valid) h = home_cell<T>(ix, qx, qy, qz);
+        TopK<T, K> top;
+        top.init();
+        if (!STAGED) {
+            if (valid) {
+                home_block<T>(ix, h, 1);
+                const HomeRuns hr = home_runs<T>(ix, h);
+                scan_home_global<T, K>(ix, hr, qx, qy, qz, dub, top);
+                knn_finish<T, K>(ix, h, qx, qy, qz, dub, s2r, sr, top);
+            }
+            emit_result<T, K, EPI>(P, ix, p, trow, tcol, lane, stage, top, valid);
+            continue;
+        }
+        // ---- 1. home blocks (half-width from the local density) and their hull
+        {
+            const uint32_t dens = valid ? home_density<T>(ix, h) : 0u;
+            const unsigned nval = __popc(__ballot_sync(0xffffffffu, valid));
+            const uint32_t dsum = __reduce_add_sync(0xffffffffu, dens);
+            const int m = home_halfwidth(P.k, nval ? (float)dsum / (float)(nval * (COARSE * COARSE)) : 0.f);
+            if (valid) home_block<T>(ix, h, m);
+        }
         const bool has_block = valid && h.hb.u0 <= h.hb.u1;
-        // ---- 1. hull of the tile's home blocks
         if (tid < HULL_ROWS) {
             sc.umin[tid] = 0x7fffffff;
             sc.umax[tid] = -1;
@@ -1305,25 +1387,21 @@ __global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS(K))
                 const int lo = __reduce_min_sync(0xffffffffu, mine ? h.hb.u0 : 0x7fffffff);
                 const int hi = __reduce_max_sync(0xffffffffu, mine ? h.hb.u1 : -1);
                 const int r0 = __shfl_sync(0xffffffffu, h.hb.v0, src), r1 = __shfl_sync(0xffffffffu, h.hb.v1, src);
-                if (lane < 3 && r0 + lane <= r1) {
+                if (lane < 2 * HOME_MAX + 1 && r0 + lane <= r1) {
                     atomicMin(&sc.umin[(r0 + lane) & (HULL_ROWS - 1)], lo);
                     atomicMax(&sc.umax[(r0 + lane) & (HULL_ROWS - 1)], hi);
                 }
                 todo &= ~grp;
             }
         }
-        // the bounds of this thread's own runs do not depend on the staging: their loads overlap steps 1 and 2
-        HomeRuns hr;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) hr.s[j] = hr.e[j] = 0, hr.v[j] = 0;
-        if (has_block) hr = home_runs<T>(ix, h);
         __syncthreads();
-        // ---- 2. warp 0 lays out and fetches the rows
-        if (warp == 0) {
+        // ---- 2. layout (every warp computes it: lanes hold rows lane and lane + 32), bulk copies (warp 0), cell table
+        {
             const int vlo = sc.vlo, vhi = sc.vhi;
             const unsigned faces = sc.faces;
             bool ok = vhi >= vlo && (vhi - vlo) < HULL_ROWS && __popc(faces) == 1;
-            uint32_t gs[2] = {0, 0}, n[2] = {0, 0};
+            uint32_t gs[2] = {0, 0}, n[2] = {0, 0}, w[2] = {0, 0};
+            const uint32_t *rowp[2] = {nullptr, nullptr};
             if (ok) {
                 const int face = __ffs(faces) - 1;
                 const FaceTable &ft = ix.fine;
@@ -1336,57 +1414,77 @@ __global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS(K))
                         const int slot = v & (HULL_ROWS - 1);
                         const int u0 = sc.umin[slot], u1 = sc.umax[slot];
                         if (u1 >= u0) {
-                            const uint32_t *row = row0 + (int64_t)v * fw;
-                            gs[j] = __ldg(row + u0);
-                            n[j] = __ldg(row + u1 + 1) - gs[j];
+                            rowp[j] = row0 + (int64_t)v * fw + u0;
+                            w[j] = (uint32_t)(u1 - u0 + 2);
+                            gs[j] = __ldg(rowp[j]);
+                            n[j] = __ldg(rowp[j] + (u1 - u0 + 1)) - gs[j];
                         }
                     }
                 }
             }
-            // exclusive prefix over the (up to 64) rows: lanes hold rows lane and lane + 32
-            uint32_t a = n[0], b = n[1];
+            // exclusive prefixes over the (up to 64) rows: records and cell-table entries
+            uint32_t a = n[0], b = n[1], ca = w[0], cb = w[1];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
-                if (lane >= o) a += ta, b += tb;
+                const uint32_t tc = __shfl_up_sync(0xffffffffu, ca, o), td = __shfl_up_sync(0xffffffffu, cb, o);
+                if (lane >= o) a += ta, b += tb, ca += tc, cb += td;
             }
             const uint32_t tot0 = __shfl_sync(0xffffffffu, a, 31), total = tot0 + __shfl_sync(0xffffffffu, b, 31);
-            ok = ok && total > 0 && total <= CAP;
+            const uint32_t ctot0 = __shfl_sync(0xffffffffu, ca, 31), ctotal = ctot0 + __shfl_sync(0xffffffffu, cb, 31);
+            ok = ok && total > 0 && total <= CAP && ctotal <= (uint32_t)STAGE_CELLS;
             if (ok) {
                 const uint32_t base[2] = {a - n[0], tot0 + b - n[1]};
-                fence_proxy_async();  // the buffer was read (generic proxy) for the previous tile
-                mbar_arrive_expect_tx(reinterpret_cast<uint64_t *>(&sc.bar), (n[0] + n[1]) * (uint32_t)sizeof(Rec<T>));
+                const uint32_t cbase[2] = {ca - w[0], ctot0 + cb - w[1]};
+                if (warp == 0) {
+                    fence_proxy_async();  // the buffer was read (generic proxy) for the previous tile
+                    mbar_arrive_expect_tx(reinterpret_cast<uint64_t *>(&sc.bar), (n[0] + n[1]) * (uint32_t)sizeof(Rec<T>));
+                }
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int v = vlo + lane + 32 * j;
                     if (v <= vhi) {
-                        const int slot = v & (HULL_ROWS - 1);
-                        sc.gstart[slot] = gs[j];
-                        sc.sbase[slot] = base[j];
-                        if (n[j])
-                            bulk_copy_g2s(srecs + base[j], ix.recs + gs[j], n[j] * (uint32_t)sizeof(Rec<T>),
-                                          reinterpret_cast<uint64_t *>(&sc.bar));
+                        if (warp == 0) {
+                            const int slot = v & (HULL_ROWS - 1);
+                            sc.gstart[slot] = gs[j];
+                            sc.sbase[slot] = base[j];
+                            sc.csbase[slot] = cbase[j];
+                            if (n[j])
+                                bulk_copy_g2s(srecs + base[j], ix.recs + gs[j], n[j] * (uint32_t)sizeof(Rec<T>),
+                                              reinterpret_cast<uint64_t *>(&sc.bar));
+                        }
                     }
+                }
+                // the cell-table stretch: warp w copies rows w, w + QROWS, ... (row r is held by lane r % 32, half r / 32)
+                const int nrows = vhi - vlo + 1;
+                for (int r = warp; r < nrows; r += QROWS) {
+                    const int src = r & 31, half = r >> 5;
+                    const uint32_t *gp = reinterpret_cast<const uint32_t *>(
+                        __shfl_sync(0xffffffffu, (unsigned long long)(half ? rowp[1] : rowp[0]), src));
+                    const uint32_t wr = __shfl_sync(0xffffffffu, half ? w[1] : w[0], src);
+                    const uint32_t cbr = __shfl_sync(0xffffffffu, half ? cbase[1] : cbase[0], src);
+                    for (uint32_t j = lane; j < wr; j += 32) scs[cbr + j] = __ldg(gp + j);
                 }
             }
             // written here and nowhere else: a thread that is slow to read it cannot see the next tile's value,
-            // because warp 0 only gets here again after two more block-wide barriers
-            if (lane == 0) sc.staged = ok ? 1 : 0;
+            // because nobody gets here again before two more block-wide barriers
+            if (tid == 0) sc.staged = ok ? 1 : 0;
         }
         __syncthreads();
         // ---- 3. search
-        TopK<T, K> top;
-        top.init();
         const bool staged = sc.staged != 0;
         if (staged) {
             mbar_wait(reinterpret_cast<uint64_t *>(&sc.bar), phase);
             phase ^= 1u;
         }
         if (valid) {
-            if (staged)
-                scan_home_staged<T, K>(sc, srecs, hr, qx, qy, qz, dub, top);
-            else
+            if (staged) {
+                scan_home_staged<T, K>(sc, srecs, scs, h, qx, qy, qz, dub, top);
+            } else {
+                home_block<T>(ix, h, 1);
+                const HomeRuns hr = home_runs<T>(ix, h);
                 scan_home_global<T, K>(ix, hr, qx, qy, qz, dub, top);
+            }
             knn_finish<T, K>(ix, h, qx, qy, qz, dub, s2r, sr, top);
         }
         emit_result<T, K, EPI>(P, ix, p, trow, tcol, lane, stage, top, valid);

@@ -1,6 +1,6 @@
 // Explicit instantiations of the search launch (query_kernel), one translation unit per (tree dtype, K, epilogue):
 //   nvcc -DPRS_INST_T=float -DPRS_INST_K=8 -DPRS_INST_EPI=2 -c prs_query_inst.cu
-// PRS_INST_EPI: 0 neighbour info, 1 nearest gather (K = 1 only), 2 Gaussian weighting.
+// PRS_INST_EPI: 0 neighbour info, 1 nearest gather (K = 1 only), 2 / 3 / 4 Gaussian weighting (f32, f64 over f32 data, f64).
 #include "prs_launch.cuh"
 
 #if !defined(PRS_INST_T) || !defined(PRS_INST_K) || !defined(PRS_INST_EPI)
@@ -8,6 +8,6 @@
 #endif
 
 namespace prs {
-template int launch_search<PRS_INST_T, PRS_INST_K, PRS_INST_EPI>(const QueryParams &, const IndexView<PRS_INST_T> &, int64_t,
+template int launch_search<PRS_INST_T, PRS_INST_K, PRS_INST_EPI>(const QueryParams &, const IndexRef<PRS_INST_T> &, int64_t,
                                                                  const uint32_t *, const uint32_t *, cudaStream_t);
 }

@@ -29,64 +29,78 @@ __device__ __forceinline__ void scan_load_items(const In *in, int64_t base, int6
     for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = scan_load(in, base + j, n);
 }
 
-template <typename In> __global__ void scan_tile_sums(const In *__restrict__ in, int64_t n, uint32_t *__restrict__ sums)
+// n_dev (optional): the length lives in device memory (index build: the size of the cell table is decided by a
+// kernel); the grid is then sized for the capacity and blocks stride over the tiles that exist.
+template <typename In>
+__global__ void scan_tile_sums(const In *__restrict__ in, int64_t n, const int64_t *__restrict__ n_dev,
+                               uint32_t *__restrict__ sums)
 {
     static_assert(SCAN_ITEMS == 8, "scan_load_items unpacks two uint4");
     __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
-    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS];
-    scan_load_items(in, base, n, v);
-    uint32_t s = 0;
+    if (n_dev) n = *n_dev;
+    const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int64_t base = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        scan_load_items(in, base, n, v);
+        uint32_t s = 0;
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) s += v[j];
+        for (int j = 0; j < SCAN_ITEMS; ++j) s += v[j];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < SCAN_THREADS / 32; ++w) t += warp_sums[w];
-        sums[blockIdx.x] = t;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < SCAN_THREADS / 32; ++w) t += warp_sums[w];
+            sums[tile] = t;
+        }
+        __syncthreads();
     }
 }
 
 // out[i] = offset[tile] + exclusive (or inclusive) prefix within the tile.  in may alias out (uint32 in place).
 template <typename In>
-__global__ void scan_tile_apply(const In *in, int64_t n, const uint32_t *__restrict__ tile_offsets, uint32_t *out,
-                                int inclusive)
+__global__ void scan_tile_apply(const In *in, int64_t n, const int64_t *__restrict__ n_dev,
+                                const uint32_t *__restrict__ tile_offsets, uint32_t *out, int inclusive)
 {
     __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
-    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS];
-    scan_load_items(in, base, n, v);
-    uint32_t s = 0;
+    if (n_dev) n = *n_dev;
+    const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int64_t base = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        scan_load_items(in, base, n, v);
+        uint32_t s = 0;
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) s += v[j];
-    uint32_t incl = s;
-    int lane = threadIdx.x & 31;
+        for (int j = 0; j < SCAN_ITEMS; ++j) s += v[j];
+        uint32_t incl = s;
+        int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_sums[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_sums[w];
-    uint32_t run = tile_offsets[blockIdx.x] + woff + (incl - s);
-    uint32_t o[SCAN_ITEMS];
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_sums[w];
+        uint32_t run = tile_offsets[tile] + woff + (incl - s);
+        uint32_t o[SCAN_ITEMS];
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        o[j] = inclusive ? run + v[j] : run;
-        run += v[j];
-    }
-    if (base + SCAN_ITEMS <= n && (reinterpret_cast<uintptr_t>(out + base) & 15) == 0) {
-        *reinterpret_cast<uint4 *>(out + base) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4 *>(out + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
-    } else {
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+            o[j] = inclusive ? run + v[j] : run;
+            run += v[j];
+        }
+        if (base + SCAN_ITEMS <= n && (reinterpret_cast<uintptr_t>(out + base) & 15) == 0) {
+            *reinterpret_cast<uint4 *>(out + base) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4 *>(out + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j)
-            if (base + j < n) out[base + j] = o[j];
+            for (int j = 0; j < SCAN_ITEMS; ++j)
+                if (base + j < n) out[base + j] = o[j];
+        }
+        __syncthreads();
     }
 }
 
@@ -94,8 +108,10 @@ __global__ void scan_tile_apply(const In *in, int64_t n, const uint32_t *__restr
 // level of the device-wide scan and for small tables, where a launch costs more than the work.
 constexpr int SMALL_SCAN_THREADS = 1024;
 static __global__ void __launch_bounds__(SMALL_SCAN_THREADS)
-    scan_small_kernel(uint32_t *data, int64_t n, int inclusive, uint32_t *total_out)
+    scan_small_kernel(uint32_t *data, int64_t n, int inclusive, uint32_t *total_out,
+                      const int64_t *__restrict__ n_dev = nullptr, int64_t per_item = 1)
 {
+    if (n_dev) n = (*n_dev + per_item - 1) / per_item;  // e.g. the tiles of a device-sized array
     __shared__ uint32_t warp_sums[SMALL_SCAN_THREADS / 32];
     __shared__ uint32_t carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -150,7 +166,7 @@ int scan_u32(const In *in, uint32_t *out, int64_t n, int inclusive, uint32_t *to
     int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t *sums = nullptr;
     PRS_CK(cudaMallocAsync((void **)&sums, sizeof(uint32_t) * (size_t)(tiles + 1), st));
-    scan_tile_sums<In><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, sums);
+    scan_tile_sums<In><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, nullptr, sums);
     PRS_CKL();
     // exclusive scan of the tile sums (recursive); sums[tiles] gets the total
     uint32_t *tot = sums + tiles;
@@ -161,9 +177,34 @@ int scan_u32(const In *in, uint32_t *out, int64_t n, int inclusive, uint32_t *to
         int rc = scan_u32<uint32_t>(sums, sums, tiles, 0, tot, st);
         if (rc != PRS_OK) return rc;
     }
-    scan_tile_apply<In><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, sums, out, inclusive);
+    scan_tile_apply<In><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, nullptr, sums, out, inclusive);
     PRS_CKL();
     if (total_dev) PRS_CK(cudaMemcpyAsync(total_dev, tot, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    PRS_CK(cudaFreeAsync(sums, st));
+    return PRS_OK;
+}
+
+// In-place scan of data[0 .. *n_dev) whose length is only known on the device (*n_dev <= cap).  Three launches with
+// fixed grids; the second level is one block over the tile sums that exist.
+inline int scan_u32_dev(uint32_t *data, int64_t cap, const int64_t *n_dev, int inclusive, cudaStream_t st)
+{
+    if (cap <= 0) return PRS_OK;
+    const int64_t tiles_cap = (cap + SCAN_TILE - 1) / SCAN_TILE;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        PRS_CK(cudaGetDevice(&dev));
+        PRS_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const unsigned grid = (unsigned)(tiles_cap < (int64_t)n_sm * 8 ? tiles_cap : (int64_t)n_sm * 8);
+    uint32_t *sums = nullptr;
+    PRS_CK(cudaMallocAsync((void **)&sums, sizeof(uint32_t) * (size_t)(tiles_cap + 1), st));
+    scan_tile_sums<uint32_t><<<grid, SCAN_THREADS, 0, st>>>(data, 0, n_dev, sums);
+    PRS_CKL();
+    scan_small_kernel<<<1, SMALL_SCAN_THREADS, 0, st>>>(sums, 0, 0, nullptr, n_dev, SCAN_TILE);
+    PRS_CKL();
+    scan_tile_apply<uint32_t><<<grid, SCAN_THREADS, 0, st>>>(data, 0, n_dev, sums, data, inclusive);
+    PRS_CKL();
     PRS_CK(cudaFreeAsync(sums, st));
     return PRS_OK;
 }

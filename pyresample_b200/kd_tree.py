@@ -281,15 +281,31 @@ def _coord_dtype(np_dtype):
 
 
 class _Index(object):
-    """Owner of a ``prs_index`` handle (stands in for the pykdtree ``KDTree`` object)."""
+    """Owner of a ``prs_index`` handle (stands in for the pykdtree ``KDTree`` object).
+
+    The build is queued without waiting for the device; the numbers that describe the result (how many points are
+    valid, the cell size, ...) live in device memory and are fetched the first time one of them is read."""
 
     def __init__(self, handle, lon_t, lat_t):
         self.handle = handle
         self._keep = (lon_t, lat_t)
-        info = (ctypes.c_int64 * 8)()
-        _cabi.check(_cabi.lib().prs_index_info(handle, info))
-        self.n_source, self.n, self.n_indexed, self.cells_per_side = info[0], info[1], info[2], info[3]
-        self.bytes, self.tree_dtype, self.coarse_per_side, self.all_valid = info[4], info[5], info[6], bool(info[7])
+        self._info = None
+
+    def _fetch(self):
+        if self._info is None:
+            info = (ctypes.c_int64 * 8)()
+            _cabi.check(_cabi.lib().prs_index_info(self.handle, info))
+            self._info = tuple(int(v) for v in info)
+        return self._info
+
+    n_source = property(lambda self: self._fetch()[0])
+    n = property(lambda self: self._fetch()[1])
+    n_indexed = property(lambda self: self._fetch()[2])
+    cells_per_side = property(lambda self: self._fetch()[3])
+    bytes = property(lambda self: self._fetch()[4])
+    tree_dtype = property(lambda self: self._fetch()[5])
+    coarse_per_side = property(lambda self: self._fetch()[6])
+    all_valid = property(lambda self: bool(self._fetch()[7]))
 
     def __del__(self):
         try:
@@ -547,23 +563,35 @@ class _Source(object):
         self.lon_t, self.lat_t = lon_t, lat_t
         tdt = np.dtype(tree_dtype) if tree_dtype is not None else self.dtype
         self.tree_dtype = tdt
-        if tdt != self.dtype:
+        # float32 lon/lat into a float64 tree (XArrayResamplerNN): the reference transforms in float32 and widens the
+        # ECEF coordinates afterwards (kd_tree.py:970-981) - the build does the same, so the arrays go in as they are
+        if tdt != self.dtype and not (self.dtype == np.float32 and tdt == np.float64):
             lon_t, lat_t = _dev(lon_t, tdt), _dev(lat_t, tdt)
+        in_dtype = _np_dtype_of(lon_t)
         handle = ctypes.c_void_p()
         excl = _dev(exclude_mask).reshape(-1) if exclude_mask is not None else None
         cover = None
         if cover_rows is not None and target_geo_def is not None:
             cover = _target_cover(target_geo_def, cover_rows, radius_of_influence, tdt)
         flags = _cabi.PRS_BUILD_COMPUTE_VALID | (_cabi.PRS_BUILD_RANKS if need_ranks else 0)
-        _cabi.check(_cabi.lib().prs_index_build(_ptr(lon_t), _ptr(lat_t), lon_t.numel(), _tree_code(tdt),
+        _cabi.check(_cabi.lib().prs_index_build(_ptr(lon_t), _ptr(lat_t), lon_t.numel(), _tree_code(in_dtype),
                                                _ptr(self.valid), ctypes.byref(box) if box is not None else None,
                                                _ptr(premask), _ptr(excl), _tree_code(tdt), int(neighbours),
                                                float(radius_of_influence), _ptr(cover), flags, ctypes.byref(handle),
                                                _stream()))
-        self.index = _Index(handle, lon_t, lat_t)
-        self.n_valid = int(self.index.n)
-        if self.n_valid == 0:  # EmptyResult of _create_resample_kdtree (kd_tree.py:480-481)
-            self.index = None
+        self._index = _Index(handle, lon_t, lat_t)
+        self.handle = handle  # for launches that need not know yet whether any source point is valid
+
+    @property
+    def n_valid(self):
+        """Number of valid source points (pykdtree's ``.n``); the first read waits for the build's plan kernel."""
+        return int(self._index.n)
+
+    @property
+    def index(self):
+        """The index, or None when no source point is valid (EmptyResult of _create_resample_kdtree,
+        kd_tree.py:480-481)."""
+        return self._index if self.n_valid > 0 else None
 
 
 class _TreeSpec(object):
@@ -1328,8 +1356,8 @@ def _resample_tensor(source, data, tgt, resample_type, radius_of_influence, neig
     output_shape = lead + ((channels,) if multi else ())
     if fill_value is None:
         raise ValueError("fill_value=None (masked output) needs numpy input")
-    if source.index is None:
-        return torch.full(output_shape, fill_value, dtype=data.dtype, device="cuda")
+    # no check for an empty index here: the kernels give every pixel the fill value then (kd_tree.py:336-341, 620-621),
+    # and asking would make the host wait for the device
     tg, n_t, keep = _make_target(source, tgt, reduce_data, radius_of_influence, rows=rows)
     if n_t == 0:  # a rank without rows
         return torch.empty(output_shape, dtype=data.dtype, device="cuda")
@@ -1338,7 +1366,7 @@ def _resample_tensor(source, data, tgt, resample_type, radius_of_influence, neig
         row_bytes = dev_data.shape[1] * dev_data.element_size()
         fill_row = torch.full((channels,), fill_value, dtype=data.dtype, device="cuda")
         out = torch.empty((n_t, channels), dtype=data.dtype, device="cuda")
-        _cabi.check(L.prs_resample_nearest(source.index.handle, ctypes.byref(tg), float(radius_of_influence),
+        _cabi.check(L.prs_resample_nearest(source.handle, ctypes.byref(tg), float(radius_of_influence),
                                            _ptr(dev_data), row_bytes, _ptr(fill_row), _ptr(out), _stream()))
         return out.reshape(output_shape)
     funcs = list(weight_funcs) if multi else [weight_funcs] * channels
@@ -1360,7 +1388,7 @@ def _resample_tensor(source, data, tgt, resample_type, radius_of_influence, neig
     sd_t = torch.empty((n_t, channels), dtype=odt, device="cuda") if with_uncert else None
     cnt_t = torch.empty((n_t, channels), dtype=odt, device="cuda") if with_uncert else None
     sig_c = (ctypes.c_double * channels)(*[float(s) for s in sigmas])
-    _cabi.check(L.prs_resample_gauss(source.index.handle, ctypes.byref(tg), int(neighbours), float(radius_of_influence),
+    _cabi.check(L.prs_resample_gauss(source.handle, ctypes.byref(tg), int(neighbours), float(radius_of_influence),
                                      _ptr(dev_data), _tree_code(ddt), channels, sig_c, float(fill_value), _ptr(out),
                                      _ptr(sd_t), _ptr(cnt_t), None, _stream()))
     del keep

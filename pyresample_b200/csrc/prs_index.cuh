@@ -142,11 +142,13 @@ template <typename T> __device__ __forceinline__ void unit_f32(T x, T y, T z, fl
 }
 
 #ifdef PRS_WITH_INDEX_BUILD  // the build itself is only compiled into prs_b200.cu
-struct BuildCounters {
-    uint32_t n_valid;    // unused by the kernels (block totals are reduced by build_plan_kernel)
+struct BuildCounters {   // zeroed before the build; every field is raised from 0 with atomicAdd / atomicMax
+    uint32_t n_valid;    // totals of pass 1 (reduced from the per-block records by build_plan_kernel)
     uint32_t n_skipped;
-    uint32_t first_inv;  // ~(raveled index of the first valid point), 0 = none: raised with atomicMax from a zeroed word
-    uint32_t pad;
+    uint32_t first_inv;  // ~(raveled index of the first valid point), 0 = none
+    uint32_t n_occ;      // occupied probe cells
+    uint32_t rect[24];   // per face: OCC_G - u0, OCC_G - v0, u1 + 1, v1 + 1 of the occupied probe cells (0 = none)
+    uint32_t done;       // blocks of build_plan_kernel that have finished their share
 };
 
 // Host copy of the index description, fetched on first use: a copy on a side stream that only waits for the plan
@@ -402,15 +404,17 @@ __global__ void __launch_bounds__(BUILD_TPB, PRS_SELECT_MIN_BLOCKS)
                     // whichever face pass 2 chooses spans the point
                     const float ax = fabsf(fx), ay = fabsf(fy), az = fabsf(fz);
                     const float lim = fmaxf(ax, fmaxf(ay, az)) * (1.0f - 1e-4f);
-#pragma unroll
-                    for (int axis = 0; axis < 3; ++axis) {
-                        const float a = axis == 0 ? ax : (axis == 1 ? ay : az);
-                        const float sv = axis == 0 ? fx : (axis == 1 ? fy : fz);
-                        const int f2 = 2 * axis + (sv < 0.f ? 1 : 0);
-                        if (a >= lim && f2 != face) {
-                            int ju, jv;
-                            cell_on_face(f2, fx, fy, fz, OCC_G, ju, jv);
-                            occ[(f2 * OCC_G + jv) * OCC_G + ju] = 1;
+                    if ((int)(ax >= lim) + (int)(ay >= lim) + (int)(az >= lim) > 1) {  // rare: within 1e-4 of an edge
+#pragma unroll 1
+                        for (int axis = 0; axis < 3; ++axis) {
+                            const float a = axis == 0 ? ax : (axis == 1 ? ay : az);
+                            const float sv = axis == 0 ? fx : (axis == 1 ? fy : fz);
+                            const int f2 = 2 * axis + (sv < 0.f ? 1 : 0);
+                            if (a >= lim && f2 != face) {
+                                int ju, jv;
+                                cell_on_face(f2, fx, fy, fz, OCC_G, ju, jv);
+                                occ[(f2 * OCC_G + jv) * OCC_G + ju] = 1;
+                            }
                         }
                     }
                     kept = true;
@@ -484,37 +488,33 @@ __device__ inline int64_t plan_tables(int G, const int rect[24], FaceTable &fine
         fine.fv0[f] = cv0 * COARSE;
         fine.fw[f] = (cu1 - cu0) * COARSE;
         fine.fh[f] = (cv1 - cv0) * COARSE;
-        nc += (int64_t)coarse.fw[f] * coarse.fh[f];
+        nc += (int64_t)(coarse.fw[f] + 1) * coarse.fh[f];  // a row holds fw + 1 row-local prefix sums
         nf += (int64_t)fine.fw[f] * fine.fh[f];
     }
     n_coarse = nc;
     return nf;
 }
 
-// The plan (one block): totals of pass 1, bounding rectangles of the occupancy probe, then the cell size - a cell
-// should hold ~lambda points, so that the 3x3 block a query scans first holds the k nearest with room to spare -
-// and the table geometry.  What index_build used to do on the host after a read-back.
-static __global__ void __launch_bounds__(1024)
-    build_plan_kernel(const uint8_t *__restrict__ occ, const uint2 *__restrict__ block_counts,
-                      const BuildCounters *__restrict__ counters, const PlanParams pp, IndexMeta *__restrict__ meta)
+// The plan: totals of pass 1, bounding rectangles of the occupancy probe (reduced by all blocks), then - in the block
+// that finishes last - the cell size (a cell should hold ~lambda points, so that the 3x3 block a query scans first
+// holds the k nearest with room to spare) and the table geometry.  What index_build used to do on the host after a
+// read-back.
+static __global__ void __launch_bounds__(256)
+    build_plan_kernel(const uint8_t *__restrict__ occ, const uint2 *__restrict__ block_counts, BuildCounters *counters,
+                      const PlanParams pp, IndexMeta *__restrict__ meta)
 {
-    __shared__ unsigned s_nv, s_ns, s_no;
-    __shared__ int s_rect[24];
-    const int tid = threadIdx.x;
-    if (tid == 0) s_nv = s_ns = s_no = 0;
-    if (tid < 24) s_rect[tid] = (tid & 3) < 2 ? (1 << 30) : -1;
-    __syncthreads();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     unsigned nv = 0, ns = 0, no = 0;
-    for (int64_t b = tid; b < pp.n_blocks; b += blockDim.x) {
+    for (int64_t b = tid; b < pp.n_blocks; b += nth) {
         const uint2 c = block_counts[b];
         nv += c.x;
         ns += c.y;
     }
     // four probe cells per thread (one 32-bit load); a warp covers one row of OCC_G = 128 cells of one face, so
-    // its bounding box is reduced in registers and costs at most four shared-memory atomics
+    // its bounding box is reduced in registers and costs at most four atomics
     static_assert(OCC_G == 128, "a warp reads exactly one row of probe cells");
     const uint32_t *occ4 = reinterpret_cast<const uint32_t *>(occ);
-    for (int w = tid; w < 6 * OCC_G * OCC_G / 4; w += blockDim.x) {
+    for (int w = tid; w < 6 * OCC_G * OCC_G / 4; w += nth) {
         const uint32_t bits = occ4[w];
         const int i = w * 4, f = i / (OCC_G * OCC_G), iv = (i / OCC_G) % OCC_G, iu = i % OCC_G;
         int u0 = 1 << 30, u1 = -1;
@@ -530,11 +530,11 @@ static __global__ void __launch_bounds__(1024)
             u0 = min(u0, __shfl_xor_sync(0xffffffffu, u0, o));
             u1 = max(u1, __shfl_xor_sync(0xffffffffu, u1, o));
         }
-        if ((tid & 31) == 0 && u1 >= 0) {
-            atomicMin(&s_rect[4 * f + 0], u0);
-            atomicMin(&s_rect[4 * f + 1], iv);
-            atomicMax(&s_rect[4 * f + 2], u1);
-            atomicMax(&s_rect[4 * f + 3], iv);
+        if ((threadIdx.x & 31) == 0 && u1 >= 0) {
+            atomicMax(&counters->rect[4 * f + 0], (uint32_t)(OCC_G - u0));
+            atomicMax(&counters->rect[4 * f + 1], (uint32_t)(OCC_G - iv));
+            atomicMax(&counters->rect[4 * f + 2], (uint32_t)(u1 + 1));
+            atomicMax(&counters->rect[4 * f + 3], (uint32_t)(iv + 1));
         }
     }
 #pragma unroll
@@ -543,29 +543,40 @@ static __global__ void __launch_bounds__(1024)
         ns += __shfl_xor_sync(0xffffffffu, ns, o);
         no += __shfl_xor_sync(0xffffffffu, no, o);
     }
-    if ((tid & 31) == 0) {
-        if (nv) atomicAdd(&s_nv, nv);
-        if (ns) atomicAdd(&s_ns, ns);
-        if (no) atomicAdd(&s_no, no);
+    if ((threadIdx.x & 31) == 0) {
+        if (nv) atomicAdd(&counters->n_valid, nv);
+        if (ns) atomicAdd(&counters->n_skipped, ns);
+        if (no) atomicAdd(&counters->n_occ, no);
     }
+    // the block that finishes last sees everybody's contributions
+    __shared__ bool last;
+    __threadfence();
     __syncthreads();
-    if (tid != 0) return;
+    if (threadIdx.x == 0) last = atomicAdd(&counters->done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last || threadIdx.x != 0) return;
+    __threadfence();
+    volatile BuildCounters *vc = counters;
     IndexMeta m;
-    m.n_valid = s_nv;
-    m.n_skipped = s_ns;
-    m.first_valid_source = counters->first_inv ? ~counters->first_inv : 0u;
-    m.n_occ = s_no;
-    m.all_valid = (int64_t)s_nv == pp.n;
+    m.n_valid = vc->n_valid;
+    m.n_skipped = vc->n_skipped;
+    m.first_valid_source = vc->first_inv ? ~vc->first_inv : 0u;
+    m.n_occ = vc->n_occ;
+    m.all_valid = (int64_t)m.n_valid == pp.n;
     m.status = 0;
     m.n_source = pp.n;
-    m.n_indexed = (int64_t)s_nv - (int64_t)s_ns;
+    m.n_indexed = (int64_t)m.n_valid - (int64_t)m.n_skipped;
     int rect[24];
-    for (int i = 0; i < 24; ++i) rect[i] = s_rect[i];
-    if (m.n_indexed <= 0) {
-        m.n_indexed = 0;
-        for (int i = 0; i < 24; ++i) rect[i] = (i & 3) < 2 ? 1 : 0;  // every face empty
+    for (int f = 0; f < 6; ++f) {
+        const uint32_t e0 = vc->rect[4 * f], e1 = vc->rect[4 * f + 1], e2 = vc->rect[4 * f + 2], e3 = vc->rect[4 * f + 3];
+        const bool any = e2 != 0 && m.n_indexed > 0;
+        rect[4 * f + 0] = any ? OCC_G - (int)e0 : 1;
+        rect[4 * f + 1] = any ? OCC_G - (int)e1 : 1;
+        rect[4 * f + 2] = any ? (int)e2 - 1 : 0;
+        rect[4 * f + 3] = any ? (int)e3 - 1 : 0;
     }
-    const double n_occ = s_no ? (double)s_no : 1.0;
+    if (m.n_indexed < 0) m.n_indexed = 0;
+    const double n_occ = m.n_occ ? (double)m.n_occ : 1.0;
     const double g = (double)OCC_G * sqrt((double)m.n_indexed / (n_occ * pp.lambda));
     int G = (int)ceil(g / COARSE) * COARSE;
     if (G < COARSE) G = COARSE;
@@ -591,11 +602,10 @@ static __global__ void __launch_bounds__(1024)
     *meta = m;
 }
 
-// zero table[0 .. n_cells + 4) and coarse[0 .. n_coarse + 4): the sizes are only known on the device
-static __global__ void build_clear_kernel(const IndexMeta *__restrict__ meta, uint32_t *__restrict__ cell_alloc,
-                                          uint32_t *__restrict__ coarse_alloc)
+// zero table[0 .. n_cells + 4): the size is only known on the device
+static __global__ void build_clear_kernel(const IndexMeta *__restrict__ meta, uint32_t *__restrict__ cell_alloc)
 {
-    const int64_t nf = meta->n_cells + 4, nc = meta->n_coarse + 4;
+    const int64_t nf = meta->n_cells + 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     // cell_alloc is 16-byte aligned: whole uint4 stores, the tail word by word
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < nf; i += stride) {
@@ -604,7 +614,6 @@ static __global__ void build_clear_kernel(const IndexMeta *__restrict__ meta, ui
         else
             for (int64_t j = i; j < nf; ++j) cell_alloc[j] = 0;
     }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += stride / 4) coarse_alloc[i] = 0;
 }
 
 __device__ __forceinline__ int64_t table_key(const FaceTable &t, int face, int iu, int iv)
@@ -625,24 +634,22 @@ __device__ __forceinline__ void source_xyz(Tin lo, Tin la, T &x, T &y, T &z)
 
 // Pass 2: exact ECEF coordinates of the kept points, their cell key and the histogram into table[key + 1].
 // tmp[i] = (x, y, z, cell key) - the record's source index is its position i, so the fourth word carries the key
-// to pass 3.  A rank of a sharded run keeps a fraction of the points ("sparse"): the coordinates are then only
-// loaded for kept points and tmp is only written for them; otherwise all loads are issued up front.
+// to pass 3.  sparse (a rank of a sharded run keeps a fraction of the points; decided on the host: a coverage mask
+// was given): the coordinates are only loaded for kept points and tmp is only written for them; otherwise all loads
+// are issued up front.
 template <typename Tin, typename T>
 __global__ void __launch_bounds__(BUILD_TPB)
     build_xyz_kernel(const Tin *__restrict__ lon, const Tin *__restrict__ lat, int64_t n,
-                     const uint8_t *__restrict__ keep, const IndexMeta *__restrict__ meta, Rec<T> *__restrict__ tmp,
-                     uint32_t *__restrict__ table)
+                     const uint8_t *__restrict__ keep, const IndexMeta *__restrict__ meta, const bool sparse,
+                     Rec<T> *__restrict__ tmp, uint32_t *__restrict__ table)
 {
+    // table geometry: one word per thread, one round trip to L2 per block
     __shared__ FaceTable ft;
-    __shared__ int s_G, s_sparse;
-    if (threadIdx.x == 0) {
-        ft = meta->fine;
-        s_G = meta->G;
-        s_sparse = meta->n_indexed * 2 < n;
-    }
+    static_assert(sizeof(FaceTable) % 4 == 0 && sizeof(FaceTable) / 4 <= BUILD_TPB, "copied word by word");
+    if (threadIdx.x < sizeof(FaceTable) / 4)
+        reinterpret_cast<uint32_t *>(&ft)[threadIdx.x] = reinterpret_cast<const uint32_t *>(&meta->fine)[threadIdx.x];
+    const int G = meta->G;
     __syncthreads();
-    const int G = s_G;
-    const bool sparse = s_sparse != 0;
     const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * BUILD_ITEMS) + threadIdx.x;
     Tin lo[BUILD_ITEMS], la[BUILD_ITEMS];
     uint8_t kp[BUILD_ITEMS];
@@ -712,9 +719,8 @@ constexpr int SCATTER_ITEMS = 4;
 template <typename T>
 __global__ void __launch_bounds__(BUILD_TPB)
     build_scatter_kernel(const Rec<T> *__restrict__ tmp, const uint8_t *__restrict__ keep, int64_t n,
-                         const IndexMeta *__restrict__ meta, uint32_t *__restrict__ table, Rec<T> *__restrict__ recs)
+                         const bool sparse, uint32_t *__restrict__ table, Rec<T> *__restrict__ recs)
 {
-    const bool sparse = meta->n_indexed * 2 < n;  // uniform over the grid
     const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * SCATTER_ITEMS) + threadIdx.x;
     Rec<T> r[SCATTER_ITEMS];
     uint8_t kp[SCATTER_ITEMS];
@@ -756,26 +762,50 @@ __global__ void __launch_bounds__(BUILD_TPB)
             store_rec(recs + pos[j], r[j].x, r[j].y, r[j].z, (uint32_t)(base + (int64_t)j * BUILD_TPB));
 }
 
-// Coarse table: number of points in each COARSE x COARSE block of fine cells, from the fine row prefix sums.
+// Coarse table: number of points in each COARSE x COARSE block of fine cells, stored as ROW-LOCAL prefix sums
+// (fw + 1 entries per row of coarse cells), so that one warp per row computes counts and prefix sums in one pass
+// and no device-wide scan is needed.  Count of the coarse cells [u0, u1] of a row: row[u1 + 1] - row[u0].
 static __global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_start, const IndexMeta *__restrict__ meta,
                                            uint32_t *__restrict__ ctable)
 {
     const FaceTable &fine = meta->fine, &coarse = meta->coarse;
-    const int64_t n_coarse = meta->n_coarse;
-    for (int64_t cc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cc < n_coarse; cc += (int64_t)gridDim.x * blockDim.x) {
-        int face = 5;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    int rows_total = 0;
 #pragma unroll
-        for (int f = 4; f >= 0; --f)
-            if (cc < coarse.base[f + 1]) face = f;
-        int64_t local = cc - coarse.base[face];
-        int cu = coarse.fu0[face] + (int)(local % coarse.fw[face]);
-        int cv = coarse.fv0[face] + (int)(local / coarse.fw[face]);
-        uint32_t tot = 0;
-        for (int r = 0; r < COARSE; ++r) {
-            int64_t k0 = table_key(fine, face, cu * COARSE, cv * COARSE + r);
-            tot += cell_start[k0 + COARSE] - cell_start[k0];
+    for (int f = 0; f < 6; ++f) rows_total += coarse.fh[f];
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows_total; r += warps) {
+        int face = 0, local = r;
+#pragma unroll
+        for (int f = 0; f < 5; ++f)
+            if (face == f && local >= coarse.fh[f]) {
+                local -= coarse.fh[f];
+                face = f + 1;
+            }
+        const int fw = coarse.fw[face];
+        uint32_t *row = ctable + coarse.base[face] + (int64_t)local * (fw + 1);
+        const int cv = coarse.fv0[face] + local;
+        uint32_t carry = 0;
+        if (lane == 0) row[0] = 0;
+        for (int i0 = 0; i0 < fw; i0 += 32) {
+            const int i = i0 + lane;
+            uint32_t tot = 0;
+            if (i < fw) {
+                const int cu = coarse.fu0[face] + i;
+                for (int q = 0; q < COARSE; ++q) {
+                    const int64_t k0 = table_key(fine, face, cu * COARSE, cv * COARSE + q);
+                    tot += cell_start[k0 + COARSE] - cell_start[k0];
+                }
+            }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (i < fw) row[i + 1] = carry + incl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        ctable[cc + 1] = tot;
     }
 }
 
@@ -821,7 +851,7 @@ int index_build_t(const Tin *lon, const Tin *lat, int64_t n, uint8_t *valid, con
     uint8_t *keep = scratch + scratch_bytes + tmp_bytes;
     // long-lived arrays, sized for the worst case
     ix->cap_cells = index_cap_cells(n);
-    ix->cap_coarse = ix->cap_cells / (COARSE * COARSE) + 8;
+    ix->cap_coarse = ix->cap_cells / (COARSE * COARSE) + 6 * 1024 + 8;  // + one entry per row of coarse cells
     PRS_CK(cudaMallocAsync((void **)&ix->meta_dev, sizeof(IndexMeta), st));
     PRS_CK(cudaMallocAsync((void **)&ix->cell_alloc, sizeof(uint32_t) * (size_t)(ix->cap_cells + 8), st));
     PRS_CK(cudaMallocAsync((void **)&ix->coarse_alloc, sizeof(uint32_t) * (size_t)(ix->cap_coarse + 8), st));
@@ -856,7 +886,7 @@ int index_build_t(const Tin *lon, const Tin *lat, int64_t n, uint8_t *valid, con
         int v = atoi(env);
         if (v >= COARSE) pp.g_max = (v / COARSE) * COARSE;
     }
-    build_plan_kernel<<<1, 1024, 0, st>>>(occ, block_counts, counters, pp, ix->meta_dev);
+    build_plan_kernel<<<96, 256, 0, st>>>(occ, block_counts, counters, pp, ix->meta_dev);
     PRS_CKL();
     PRS_CK(cudaEventRecord(ix->planned, st));
     static int n_sm = 0;
@@ -865,7 +895,7 @@ int index_build_t(const Tin *lon, const Tin *lat, int64_t n, uint8_t *valid, con
         PRS_CK(cudaGetDevice(&dev));
         PRS_CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    build_clear_kernel<<<n_sm * 8, TPB, 0, st>>>(ix->meta_dev, ix->cell_alloc, ix->coarse_alloc);
+    build_clear_kernel<<<n_sm * 8, TPB, 0, st>>>(ix->meta_dev, ix->cell_alloc);
     PRS_CKL();
     if (ix->rank) {
         // rank of every source point among the valid ones = the index space of index_array (kd_tree.py:635)
@@ -873,18 +903,17 @@ int index_build_t(const Tin *lon, const Tin *lat, int64_t n, uint8_t *valid, con
         if (rc != PRS_OK) return rc;
     }
     // pass 2 + scan + pass 3
-    build_xyz_kernel<Tin, T><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, ix->meta_dev, tmp, ix->cell_start);
+    const bool sparse = cover != nullptr;  // a rank of a sharded run: most points are skipped
+    build_xyz_kernel<Tin, T><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, ix->meta_dev, sparse, tmp, ix->cell_start);
     PRS_CKL();
     rc = scan_u32_dev(ix->cell_start + 1, ix->cap_cells, &ix->meta_dev->n_cells, 0, st);
     if (rc != PRS_OK) return rc;
     const unsigned scatter_blocks = (unsigned)((n + BUILD_TPB * SCATTER_ITEMS - 1) / (BUILD_TPB * SCATTER_ITEMS));
-    build_scatter_kernel<T><<<scatter_blocks, BUILD_TPB, 0, st>>>(tmp, keep, n, ix->meta_dev, ix->cell_start, (Rec<T> *)ix->recs);
+    build_scatter_kernel<T><<<scatter_blocks, BUILD_TPB, 0, st>>>(tmp, keep, n, sparse, ix->cell_start, (Rec<T> *)ix->recs);
     PRS_CKL();
-    // coarse table
+    // coarse table (counts + row-local prefix sums in one kernel)
     build_coarse_kernel<<<n_sm * 4, TPB, 0, st>>>(ix->cell_start, ix->meta_dev, ix->coarse_start);
     PRS_CKL();
-    rc = scan_u32_dev(ix->coarse_start + 1, ix->cap_coarse, &ix->meta_dev->n_coarse, 1, st);
-    if (rc != PRS_OK) return rc;
     timer.mark("all queued");
     return PRS_OK;
 }

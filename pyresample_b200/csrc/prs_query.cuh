@@ -28,7 +28,7 @@ constexpr int STAGE_ROW_BYTES = 64; // nearest rows up to this size are staged t
 // Resident blocks per SM asked of the compiler for query_kernel (32 * QROWS threads): the search is latency bound,
 // so occupancy beats registers up to k = 8 (64 registers, measured on C2/C3/C5); wider top-k lists get more.
 #ifndef PRS_QUERY_MIN_BLOCKS
-#define PRS_QUERY_MIN_BLOCKS(K) (((K) <= 8 ? 32 : (K) <= 16 ? 24 : 16) / PRS_QROWS)
+#define PRS_QUERY_MIN_BLOCKS(K) (((K) <= 8 ? 32 : 16) / PRS_QROWS)
 #endif
 
 // Records fetched together in the candidate loop of the hot path.
@@ -107,6 +107,54 @@ template <typename T, int K> struct TopK {
         }
     }
     __device__ __forceinline__ bool full() const { return id[K - 1] != PRS_NONE; }
+
+    // ---- branch-free bulk insertion (wide lists): a chunk of CH candidates, none of them listed yet, is sorted by a
+    // bitonic network and merged into the list by a bitonic merge.  Every lane of a warp does the same work whatever
+    // its data, whereas offer() makes the whole warp walk the insertion code whenever ANY lane accepts a candidate -
+    // for k = 16 that was 60 % of the search's instructions at a third of the lanes active.
+    // (a, ia) / (b, ib) -> ordered so that the first is before the second when up, the reverse otherwise
+    static __device__ __forceinline__ void cex(T &a, uint32_t &ia, T &b, uint32_t &ib, bool up)
+    {
+        const bool sw = up ? before(b, ib, a, ia) : before(a, ia, b, ib);
+        const T ta = sw ? b : a, tb = sw ? a : b;
+        const uint32_t tia = sw ? ib : ia, tib = sw ? ia : ib;
+        a = ta, b = tb, ia = tia, ib = tib;
+    }
+    // cd / ci: CH candidates (CH a power of two <= K); entries that are no candidates hold (inf, PRS_NONE)
+    template <int CH> __device__ __forceinline__ void merge_chunk(T (&cd)[CH], uint32_t (&ci)[CH])
+    {
+        static_assert(CH <= K && (CH & (CH - 1)) == 0 && (K & (K - 1)) == 0, "power-of-two sizes");
+        // bitonic sort of the chunk, DESCENDING
+#pragma unroll
+        for (int k = 2; k <= CH; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const int l = i ^ j;
+                    if (l > i) cex(cd[i], ci[i], cd[l], ci[l], (i & k) != 0);
+                }
+            }
+        }
+        // list ascending, chunk descending (aligned with the END of the list): the element-wise minimum of the two holds
+        // the K smallest of their union as a bitonic sequence ...
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int t = K - CH + i;
+            const bool take = before(cd[i], ci[i], d[t], id[t]);
+            d[t] = take ? cd[i] : d[t];
+            id[t] = take ? ci[i] : id[t];
+        }
+        // ... which a bitonic merge sorts (ascending)
+#pragma unroll
+        for (int j = K >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const int l = i ^ j;
+                if (l > i) cex(d[i], id[i], d[l], id[l], true);
+            }
+        }
+    }
 };
 
 // What the kernels know about the index: the device-resident description (IndexMeta, copied into shared memory by
@@ -232,8 +280,10 @@ __device__ __forceinline__ uint32_t coarse_rect_count(const FaceTable &ct, const
 {
     if (!clip_rect(ct, f, c)) return 0;
     uint32_t total = 0;
-    const uint32_t *row = coarse_start + ct.base[f] + (int64_t)(c.v0 - ct.fv0[f]) * ct.fw[f] - ct.fu0[f];
-    for (int iv = c.v0; iv <= c.v1; ++iv, row += ct.fw[f]) total += __ldg(row + c.u1 + 1) - __ldg(row + c.u0);
+    // rows of fw + 1 row-local prefix sums (build_coarse_kernel)
+    const int pitch = ct.fw[f] + 1;
+    const uint32_t *row = coarse_start + ct.base[f] + (int64_t)(c.v0 - ct.fv0[f]) * pitch - ct.fu0[f];
+    for (int iv = c.v0; iv <= c.v1; ++iv, row += pitch) total += __ldg(row + c.u1 + 1) - __ldg(row + c.u0);
     return total;
 }
 
@@ -295,11 +345,15 @@ __device__ __forceinline__ void scan_rect(const IndexView<T> &ix, int face, cons
     }
 }
 
-// General search: continues after the 3x3 block `hb` around the home cell (cu, cv) has been scanned.
-//   phase 0: grow the block (half-width m = 3, 7, ...) until it holds k candidates or covers the radius;
+// General search: continues after the home block `hb` around the home cell (cu, cv) has been scanned.
+//   phase 0: grow the block ring by ring until it holds k candidates or covers the radius.  The rings are thin (two
+//            cells): a point OUTSIDE the swath has its k nearest in the sliver where the block first cuts into the
+//            swath, and a block that doubles each time would drag in thousands of candidates behind it (those points
+//            were 4 % of C3's pixels and most of its search time).  Empty space is crossed 16 cells at a time after a
+//            look at the coarse table;
 //   phase 1: on the home face, visit every cell that can still beat (or tie) the k-th distance;
 //   phase 2: the same on the other faces the cap reaches (only near cube edges).
-// One loop with a single scan site.  This is the cold path (sparse data, swath edges, large k, cube edges).
+// One loop with a single scan site.  This is the cold path (sparse data, swath edges, cube edges).
 template <typename T, int K>
 __device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T qx, T qy, T qz, T dub, float s2r, float sr,
                                                       TopK<T, K> top, CellRect hb, int hface, int cu, int cv)
@@ -316,7 +370,8 @@ __device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T 
         return top;
     CellRect rr = bounds_to_cells(hbnd, G);  // everything within the radius on the home face
     int phase = top.full() ? 1 : (clip_rect(ix.fine, hface, rr) ? 0 : 1);
-    int m = 3;
+    // half-width of what has been visited around (cu, cv)
+    int m = hb.u0 <= hb.u1 ? max(max(cu - hb.u0, hb.u1 - cu), max(cv - hb.v0, hb.v1 - cv)) : 0;
     int f = 0;
     float s2b = s2r, sb = sr;
     if (top.full()) {
@@ -329,14 +384,30 @@ __device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T 
         c.u0 = c.v0 = 1;
         c.u1 = c.v1 = 0;
         int face = hface;
-        bool skip = false, scan = false;
+        bool skip = false, scan = false, record = false;
         if (phase == 0) {
+            // look ahead: when the coarse cells under the block 16 cells further out hold no point at all, that whole
+            // block is crossed without a scan
+            CellRect far;
+            far.u0 = max(cu - m - COARSE, rr.u0), far.u1 = min(cu + m + COARSE, rr.u1);
+            far.v0 = max(cv - m - COARSE, rr.v0), far.v1 = min(cv + m + COARSE, rr.v1);
+            bool empty_ahead = false;
+            if (far.u0 <= far.u1 && far.v0 <= far.v1) {
+                CellRect cc;
+                cc.u0 = far.u0 / COARSE, cc.u1 = far.u1 / COARSE, cc.v0 = far.v0 / COARSE, cc.v1 = far.v1 / COARSE;
+                empty_ahead = coarse_rect_count(ix.coarse, ix.coarse_start, hface, cc) == 0;
+            }
+            m += empty_ahead ? COARSE : 2;
             c.u0 = max(cu - m, rr.u0);
             c.u1 = min(cu + m, rr.u1);
             c.v0 = max(cv - m, rr.v0);
             c.v1 = min(cv + m, rr.v1);
-            scan = c.u0 <= c.u1 && c.v0 <= c.v1;
             skip = hb.u0 <= hb.u1;
+            // the visited region is tracked as one rectangle; a block that does not contain the previous one is
+            // simply not recorded (its cells may be offered again later - TopK::offer drops duplicates)
+            record = c.u0 <= c.u1 && c.v0 <= c.v1 &&
+                     (hb.u0 > hb.u1 || (c.u0 <= hb.u0 && c.u1 >= hb.u1 && c.v0 <= hb.v0 && c.v1 >= hb.v1));
+            scan = c.u0 <= c.u1 && c.v0 <= c.v1 && !empty_ahead;
         } else if (phase == 1) {
             float b[4];
             face_bounds(hface, fx, fy, fz, s2b, sb, b);
@@ -354,17 +425,13 @@ __device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T 
         }
         if (scan) scan_rect<T, K>(ix, face, c, skip, hb, qx, qy, qz, dub, top);
         if (phase == 0) {
-            // the visited region is tracked as one rectangle; a block that does not contain the previous one is
-            // simply not recorded (its cells may be offered again later - TopK::offer drops duplicates)
-            if (scan && (hb.u0 > hb.u1 || (c.u0 <= hb.u0 && c.u1 >= hb.u1 && c.v0 <= hb.v0 && c.v1 >= hb.v1))) hb = c;
+            if (record) hb = c;
             if (top.full() || (cu - m <= rr.u0 && cu + m >= rr.u1 && cv - m <= rr.v0 && cv + m >= rr.v1)) {
                 phase = 1;
                 if (top.full()) {
                     s2b = cap_s2<T>(top.d[K - 1]);
                     sb = sqrtf(s2b);
                 }
-            } else {
-                m = 2 * m + 1;
             }
         } else if (phase == 1) {
             if (single) break;
@@ -437,7 +504,7 @@ struct StageCtx {
     int umin[HULL_ROWS], umax[HULL_ROWS];
     uint32_t gstart[HULL_ROWS];      // index of the first staged record of the row in recs[]
     uint32_t sbase[HULL_ROWS];       // ... and its slot in the record buffer
-    uint32_t csbase[HULL_ROWS];      // slot of cell_start[row][umin] in the staged cell-table stretch
+    int csoff[HULL_ROWS];            // staged cell-table stretch: cell_start[row][u] sits at scs[csoff + u]
     int vlo, vhi;
     unsigned faces;
     int staged;                      // 1: the tile's candidates are (being) staged
@@ -480,7 +547,7 @@ template <typename T> __device__ __forceinline__ uint32_t home_density(const Ind
     const FaceTable &ct = ix.coarse;
     const int cu = h.cu / COARSE, cv = h.cv / COARSE, f = h.face;
     if (ct.fw[f] == 0 || cu < ct.fu0[f] || cu >= ct.fu0[f] + ct.fw[f] || cv < ct.fv0[f] || cv >= ct.fv0[f] + ct.fh[f]) return 0;
-    const uint32_t *p = ix.coarse_start + ct.base[f] + (int64_t)(cv - ct.fv0[f]) * ct.fw[f] + (cu - ct.fu0[f]);
+    const uint32_t *p = ix.coarse_start + ct.base[f] + (int64_t)(cv - ct.fv0[f]) * (ct.fw[f] + 1) + (cu - ct.fu0[f]);
     return __ldg(p + 1) - __ldg(p);
 }
 
@@ -560,13 +627,63 @@ __device__ __forceinline__ Rec<double> lds_rec(const Rec<double> *p)
 }
 
 // Hot path, records and cell bounds staged in shared memory: the rows of the home block, the point's own row first,
-// then outwards.
+// then outwards.  Lists of 16 or more are filled chunk-wise through the sorting network (TopK::merge_chunk).
+#ifndef PRS_CHUNK_MIN_K
+#define PRS_CHUNK_MIN_K 16
+#endif
 template <typename T, int K>
 __device__ __forceinline__ void scan_home_staged(const StageCtx &sc, const Rec<T> *srecs, const uint32_t *scs,
                                                  const Home &h, T qx, T qy, T qz, T dub, TopK<T, K> &top)
 {
     if (h.hb.u0 > h.hb.u1) return;  // home block outside the table
     const int m = max(h.cv - h.hb.v0, h.hb.v1 - h.cv);
+    if (K >= PRS_CHUNK_MIN_K) {
+        constexpr int CH = K < 16 ? K : 16;
+        // a cursor over the candidates of all rows: row `step` (0: cv; 1: cv - 1; 2: cv + 1; ...), records [i, e)
+        int step = -1;
+        uint32_t i = 0, e = 0;
+        const Rec<T> *run = srecs;
+        bool more = true;
+#pragma unroll 1
+        while (more) {
+            T cd[CH];
+            uint32_t ci[CH];
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                cd[j] = Ar<T>::inf();
+                ci[j] = PRS_NONE;
+                while (more && i >= e) {  // next row with records
+                    ++step;
+                    if (step > 2 * m) {
+                        more = false;
+                        break;
+                    }
+                    const int off = (step + 1) >> 1;
+                    const int v = (step & 1) ? h.cv - off : h.cv + off;
+                    if (v < h.hb.v0 || v > h.hb.v1) continue;
+                    const int slot = v & (HULL_ROWS - 1);
+                    const uint32_t *cs = scs + sc.csoff[slot];
+                    i = cs[h.hb.u0];
+                    e = cs[h.hb.u1 + 1];
+                    run = srecs + sc.sbase[slot] - sc.gstart[slot];
+                }
+                if (more) {
+                    const Rec<T> r = lds_rec(run + i);
+                    ++i;
+                    const T d2 = dist2<T>(qx, qy, qz, r.x, r.y, r.z);
+                    // strict radius test in the tree dtype (pykdtree); what cannot enter the list is left out of the sort
+                    if (d2 < dub && TopK<T, K>::before(d2, r.idx, top.d[K - 1], top.id[K - 1])) {
+                        cd[j] = d2;
+                        ci[j] = r.idx;
+                        any = true;
+                    }
+                }
+            }
+            if (__any_sync(__activemask(), any)) top.template merge_chunk<CH>(cd, ci);
+        }
+        return;
+    }
 #pragma unroll 1
     for (int step = 0; step <= 2 * m; ++step) {
         // step 0: cv; 1: cv - 1; 2: cv + 1; 3: cv - 2; ...
@@ -574,7 +691,7 @@ __device__ __forceinline__ void scan_home_staged(const StageCtx &sc, const Rec<T
         const int v = (step & 1) ? h.cv - off : h.cv + off;
         if (v < h.hb.v0 || v > h.hb.v1) continue;
         const int slot = v & (HULL_ROWS - 1);
-        const uint32_t *cs = scs + sc.csbase[slot] - sc.umin[slot];
+        const uint32_t *cs = scs + sc.csoff[slot];
         const uint32_t s = cs[h.hb.u0], e = cs[h.hb.u1 + 1];
         const Rec<T> *run = srecs + sc.sbase[slot] - sc.gstart[slot];
 #pragma unroll 1
@@ -1446,9 +1563,11 @@ __global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS(K))
                     if (v <= vhi) {
                         if (warp == 0) {
                             const int slot = v & (HULL_ROWS - 1);
+                            // (umin / umax are reset for the next tile by whoever gets there first: what the scan
+                            // needs of them is kept in fields that are only written here)
                             sc.gstart[slot] = gs[j];
                             sc.sbase[slot] = base[j];
-                            sc.csbase[slot] = cbase[j];
+                            sc.csoff[slot] = (int)cbase[j] - sc.umin[slot];
                             if (n[j])
                                 bulk_copy_g2s(srecs + base[j], ix.recs + gs[j], n[j] * (uint32_t)sizeof(Rec<T>),
                                               reinterpret_cast<uint64_t *>(&sc.bar));

@@ -100,87 +100,112 @@ struct WeightedParams {
 
 // get_sample_from_neighbour_info('custom') on precomputed neighbour info, runtime k (kd_tree.py:741-859).
 // Tw: dtype of distances / explicit weights; Td: data dtype; Ta: accumulation and output dtype.
-// Channels are processed four at a time so that a neighbour's row is read with one 16-byte load; per channel the
-// neighbours are accumulated in order i = 0..k-1 like the reference's Python loop.
-template <typename Tw, typename Td, typename Ta> __global__ void gather_weighted_kernel(const WeightedParams P)
+// One thread per (target point, group of four channels): the threads of a point sit in neighbouring lanes, so a
+// neighbour's row is read as one contiguous segment (16 bytes per lane), index and weight loads are broadcasts, and the
+// output row is written contiguously.  Per channel the neighbours are accumulated in order i = 0..k-1 like the
+// reference's Python loop; four neighbours are fetched at a time so that their loads are in flight together.
+template <typename Tw, typename Td, typename Ta>
+__global__ void __launch_bounds__(256) gather_weighted_kernel(const WeightedParams P)
 {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n_out) return;
     const int k = P.k, C = P.channels;
+    const int groups = (C + 3) >> 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = t / groups;
+    if (p >= P.n_out) return;
+    const int c0 = (int)(t - p * groups) * 4;
+    const int nc = min(4, C - c0);
     const uint32_t *idx = P.index + (size_t)p * k;
     const bool want_uncert = P.stddev_out != nullptr;
     const Td *data = (const Td *)P.data;
     const bool vec_ok = (C & 3) == 0 && ((reinterpret_cast<uintptr_t>(data) & 15) == 0);
     const Tw *dist = P.weights ? nullptr : (const Tw *)P.dist + (size_t)p * k;
-    int count = 0;
-    for (int i = 0; i < k; ++i) count += idx[i] < P.n_valid ? 1 : 0;
-    for (int c0 = 0; c0 < C; c0 += 4) {
-        const int nc = min(4, C - c0);
-        const Tw *wplane[4] = {nullptr, nullptr, nullptr, nullptr};
-        Tw s2c[4] = {1, 1, 1, 1};
-        bool same_w = true;  // the four channels share one weight (same plane / same sigma): evaluate it once
+    const Tw *wplane[4] = {nullptr, nullptr, nullptr, nullptr};
+    Tw s2c[4] = {1, 1, 1, 1};
+    bool same_w = true;  // the four channels share one weight (same plane / same sigma): evaluate it once
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = c0 + min(j, nc - 1);
-            if (P.weights)
-                wplane[j] = (const Tw *)P.weights + ((size_t)P.plane_of_channel[c] * P.n_out + p) * k;
-            else
-                s2c[j] = (Tw)P.sigma2[c];
-            same_w = same_w && wplane[j] == wplane[0] && s2c[j] == s2c[0];
-        }
-        Ta res[4] = {0, 0, 0, 0}, norm[4] = {0, 0, 0, 0};
-        for (int pass = 0; pass < (want_uncert ? 2 : 1); ++pass) {
-            Ta nsq[4] = {0, 0, 0, 0}, sd[4] = {0, 0, 0, 0};
-            for (int i = 0; i < k; ++i) {
-                const uint32_t r = idx[i];
-                const bool missing = r >= P.n_valid;
-                const uint32_t s = missing ? P.first_valid_source : (P.rank_to_source ? __ldg(P.rank_to_source + r) : r);
-                Td v[4];
-                load_channels<Td>(data + (size_t)s * C + c0, nc, vec_ok, v);
-                Tw d2 = 0;
-                if (!P.weights) {
-                    const Tw d = missing ? (Tw)1 : dist[i];
-                    d2 = Ar<Tw>::mul(d, d);
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + min(j, nc - 1);
+        if (P.weights)
+            wplane[j] = (const Tw *)P.weights + ((size_t)P.plane_of_channel[c] * P.n_out + p) * k;
+        else
+            s2c[j] = (Tw)P.sigma2[c];
+        same_w = same_w && wplane[j] == wplane[0] && s2c[j] == s2c[0];
+    }
+    Ta res[4] = {0, 0, 0, 0}, norm[4] = {0, 0, 0, 0};
+    int count = 0;
+    for (int pass = 0; pass < (want_uncert ? 2 : 1); ++pass) {
+        Ta nsq[4] = {0, 0, 0, 0}, sd[4] = {0, 0, 0, 0};
+        for (int i0 = 0; i0 < k; i0 += 4) {
+            uint32_t r[4];
+            bool missing[4];
+            Td v[4][4];
+            Ta w[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r[u] = i0 + u < k ? idx[i0 + u] : 0xFFFFFFFFu;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                missing[u] = r[u] >= P.n_valid;
+                const uint32_t s = missing[u] ? P.first_valid_source : (P.rank_to_source ? __ldg(P.rank_to_source + r[u]) : r[u]);
+                if (i0 + u < k) {
+                    load_channels<Td>(data + (size_t)s * C + c0, nc, vec_ok, v[u]);
+                    Tw d2 = 0;
+                    if (!P.weights) {
+                        const Tw d = missing[u] ? (Tw)1 : dist[i0 + u];
+                        d2 = Ar<Tw>::mul(d, d);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j > 0 && same_w)
+                            w[u][j] = w[u][0];
+                        else
+                            w[u][j] = P.weights ? (Ta)wplane[j][i0 + u] : (Ta)Ar<Tw>::exp(Ar<Tw>::div(-d2, s2c[j]));
+                    }
                 }
-                Ta w0 = 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u >= k) continue;
+                if (pass == 0 && !missing[u]) ++count;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    Ta w;
-                    if (j > 0 && same_w)
-                        w = w0;
-                    else
-                        w = P.weights ? (Ta)wplane[j][i] : (Ta)Ar<Tw>::exp(Ar<Tw>::div(-d2, s2c[j]));
-                    if (j == 0) w0 = w;
-                    const Ta wt = missing ? Ar<Ta>::mul((Ta)0, w) : w;
+                    const Ta wt = missing[u] ? Ar<Ta>::mul((Ta)0, w[u][j]) : w[u][j];
                     if (pass == 0) {
-                        res[j] = Ar<Ta>::add(res[j], Ar<Ta>::mul(wt, (Ta)v[j]));
+                        res[j] = Ar<Ta>::add(res[j], Ar<Ta>::mul(wt, (Ta)v[u][j]));
                         norm[j] = Ar<Ta>::add(norm[j], wt);
                     } else {
                         nsq[j] = Ar<Ta>::add(nsq[j], Ar<Ta>::mul(wt, wt));
-                        const Ta val = missing ? Ar<Ta>::mul((Ta)0, (Ta)v[j]) : (Ta)v[j];
+                        const Ta val = missing[u] ? Ar<Ta>::mul((Ta)0, (Ta)v[u][j]) : (Ta)v[u][j];
                         const Ta dv = Ar<Ta>::sub(val, res[j]);
                         sd[j] = Ar<Ta>::add(sd[j], Ar<Ta>::mul(wt, Ar<Ta>::mul(dv, dv)));
                     }
                 }
             }
-            if (pass == 0) {
+        }
+        if (pass == 0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    // norm > 0 is False for NaN as well, like numpy's boolean mask (kd_tree.py:807-809)
-                    res[j] = (norm[j] > 0) ? Ar<Ta>::div(res[j], norm[j]) : (Ta)P.fill;
-                    if (j < nc) ((Ta *)P.out)[(size_t)p * C + c0 + j] = res[j];
-                }
+            for (int j = 0; j < 4; ++j) {
+                // norm > 0 is False for NaN as well, like numpy's boolean mask (kd_tree.py:807-809)
+                res[j] = (norm[j] > 0) ? Ar<Ta>::div(res[j], norm[j]) : (Ta)P.fill;
+            }
+            Ta *o = (Ta *)P.out + (size_t)p * C + c0;
+            if (nc == 4 && sizeof(Ta) == 8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                reinterpret_cast<double2 *>(o)[0] = make_double2((double)res[0], (double)res[1]);
+                reinterpret_cast<double2 *>(o)[1] = make_double2((double)res[2], (double)res[3]);
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j < nc) {
-                        const Ta sdv =
-                            count > 1 ? Ar<Ta>::sqrt(Ar<Ta>::mul(
-                                            Ar<Ta>::div(norm[j], Ar<Ta>::sub(Ar<Ta>::mul(norm[j], norm[j]), nsq[j])), sd[j]))
-                                      : Ar<Ta>::nan();
-                        ((Ta *)P.stddev_out)[(size_t)p * C + c0 + j] = sdv;
-                        ((Ta *)P.count_out)[(size_t)p * C + c0 + j] = (Ta)count;
-                    }
+                for (int j = 0; j < 4; ++j)
+                    if (j < nc) o[j] = res[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nc) {
+                    const Ta sdv =
+                        count > 1 ? Ar<Ta>::sqrt(Ar<Ta>::mul(
+                                        Ar<Ta>::div(norm[j], Ar<Ta>::sub(Ar<Ta>::mul(norm[j], norm[j]), nsq[j])), sd[j]))
+                                  : Ar<Ta>::nan();
+                    ((Ta *)P.stddev_out)[(size_t)p * C + c0 + j] = sdv;
+                    ((Ta *)P.count_out)[(size_t)p * C + c0 + j] = (Ta)count;
                 }
             }
         }
@@ -810,7 +835,7 @@ int prs_gather_weighted(const uint32_t *index, const void *dist, int64_t n_out, 
     P.sigma2 = s2_dev;
     bool w64 = weight_dtype == PRS_F64, d64 = data_dtype == PRS_F64;
     bool acc64 = channels > 1 || w64 || d64;
-    unsigned grid = blocks_for(n_out);
+    unsigned grid = blocks_for(n_out * ((channels + 3) / 4));
     if (!acc64)
         gather_weighted_kernel<float, float, float><<<grid, TPB, 0, st>>>(P);
     else if (w64 && d64)

@@ -373,6 +373,11 @@ __device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T 
     // half-width of what has been visited around (cu, cv)
     int m = hb.u0 <= hb.u1 ? max(max(cu - hb.u0, hb.u1 - cu), max(cv - hb.v0, hb.v1 - cv)) : 0;
     int f = 0;
+    // phase 0 walks a ring as four strips around the visited block (sub = 0..3: above, below, left, right), each only
+    // when the coarse table shows points under it; sub == 4: grow the block; sub == 5: the whole new block at once
+    int sub = 4;
+    CellRect cnew;
+    cnew.u0 = cnew.v0 = 1, cnew.u1 = cnew.v1 = 0;
     float s2b = s2r, sb = sr;
     if (top.full()) {
         s2b = cap_s2<T>(top.d[K - 1]);
@@ -384,30 +389,58 @@ __device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T 
         c.u0 = c.v0 = 1;
         c.u1 = c.v1 = 0;
         int face = hface;
-        bool skip = false, scan = false, record = false;
+        bool skip = false, scan = false;
         if (phase == 0) {
-            // look ahead: when the coarse cells under the block 16 cells further out hold no point at all, that whole
-            // block is crossed without a scan
-            CellRect far;
-            far.u0 = max(cu - m - COARSE, rr.u0), far.u1 = min(cu + m + COARSE, rr.u1);
-            far.v0 = max(cv - m - COARSE, rr.v0), far.v1 = min(cv + m + COARSE, rr.v1);
-            bool empty_ahead = false;
-            if (far.u0 <= far.u1 && far.v0 <= far.v1) {
-                CellRect cc;
-                cc.u0 = far.u0 / COARSE, cc.u1 = far.u1 / COARSE, cc.v0 = far.v0 / COARSE, cc.v1 = far.v1 / COARSE;
-                empty_ahead = coarse_rect_count(ix.coarse, ix.coarse_start, hface, cc) == 0;
+            if (sub == 4) {
+                // look ahead: when the coarse cells under the block 16 cells further out hold no point at all, that
+                // whole block is crossed without a scan
+                CellRect far;
+                far.u0 = max(cu - m - COARSE, rr.u0), far.u1 = min(cu + m + COARSE, rr.u1);
+                far.v0 = max(cv - m - COARSE, rr.v0), far.v1 = min(cv + m + COARSE, rr.v1);
+                bool empty_ahead = false;
+                if (far.u0 <= far.u1 && far.v0 <= far.v1) {
+                    CellRect cc;
+                    cc.u0 = far.u0 / COARSE, cc.u1 = far.u1 / COARSE, cc.v0 = far.v0 / COARSE, cc.v1 = far.v1 / COARSE;
+                    empty_ahead = coarse_rect_count(ix.coarse, ix.coarse_start, hface, cc) == 0;
+                }
+                m += empty_ahead ? COARSE : 2;
+                cnew.u0 = max(cu - m, rr.u0);
+                cnew.u1 = min(cu + m, rr.u1);
+                cnew.v0 = max(cv - m, rr.v0);
+                cnew.v1 = min(cv + m, rr.v1);
+                const bool nonempty = cnew.u0 <= cnew.u1 && cnew.v0 <= cnew.v1;
+                const bool around = nonempty && hb.u0 <= hb.u1 && cnew.u0 <= hb.u0 && cnew.u1 >= hb.u1 &&
+                                    cnew.v0 <= hb.v0 && cnew.v1 >= hb.v1;
+                if (empty_ahead || !nonempty) {
+                    sub = 5;  // nothing to scan
+                } else if (around) {
+                    sub = 0;  // four strips around the visited block
+                } else {
+                    sub = 5;  // no visited block to go around (or it sticks out of the radius): the whole block
+                    c = cnew;
+                    skip = hb.u0 <= hb.u1;
+                    scan = true;
+                }
             }
-            m += empty_ahead ? COARSE : 2;
-            c.u0 = max(cu - m, rr.u0);
-            c.u1 = min(cu + m, rr.u1);
-            c.v0 = max(cv - m, rr.v0);
-            c.v1 = min(cv + m, rr.v1);
-            skip = hb.u0 <= hb.u1;
-            // the visited region is tracked as one rectangle; a block that does not contain the previous one is
-            // simply not recorded (its cells may be offered again later - TopK::offer drops duplicates)
-            record = c.u0 <= c.u1 && c.v0 <= c.v1 &&
-                     (hb.u0 > hb.u1 || (c.u0 <= hb.u0 && c.u1 >= hb.u1 && c.v0 <= hb.v0 && c.v1 >= hb.v1));
-            scan = c.u0 <= c.u1 && c.v0 <= c.v1 && !empty_ahead;
+            if (sub < 4) {
+                c = cnew;
+                if (sub == 0)
+                    c.v1 = hb.v0 - 1;
+                else if (sub == 1)
+                    c.v0 = hb.v1 + 1;
+                else {
+                    c.v0 = hb.v0, c.v1 = hb.v1;
+                    if (sub == 2)
+                        c.u1 = hb.u0 - 1;
+                    else
+                        c.u0 = hb.u1 + 1;
+                }
+                if (c.u0 <= c.u1 && c.v0 <= c.v1) {
+                    CellRect cc;
+                    cc.u0 = c.u0 / COARSE, cc.u1 = c.u1 / COARSE, cc.v0 = c.v0 / COARSE, cc.v1 = c.v1 / COARSE;
+                    scan = coarse_rect_count(ix.coarse, ix.coarse_start, hface, cc) != 0;
+                }
+            }
         } else if (phase == 1) {
             float b[4];
             face_bounds(hface, fx, fy, fz, s2b, sb, b);
@@ -425,7 +458,16 @@ __device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T 
         }
         if (scan) scan_rect<T, K>(ix, face, c, skip, hb, qx, qy, qz, dub, top);
         if (phase == 0) {
-            if (record) hb = c;
+            if (sub < 3) {
+                ++sub;
+                continue;
+            }
+            // the ring is done.  The visited region is tracked as one rectangle; a block that does not contain the
+            // previous one is simply not recorded (its cells may be offered again later - TopK::offer drops duplicates)
+            if (cnew.u0 <= cnew.u1 && cnew.v0 <= cnew.v1 &&
+                (hb.u0 > hb.u1 || (cnew.u0 <= hb.u0 && cnew.u1 >= hb.u1 && cnew.v0 <= hb.v0 && cnew.v1 >= hb.v1)))
+                hb = cnew;
+            sub = 4;
             if (top.full() || (cu - m <= rr.u0 && cu + m >= rr.u1 && cv - m <= rr.v0 && cv + m >= rr.v1)) {
                 phase = 1;
                 if (top.full()) {

@@ -195,3 +195,27 @@ def test_xarray_resampler_nn_reference_literals(kd, monkeypatch):
     fallback.get_neighbour_info()
     assert np.nansum(_values(fallback.get_sample_from_neighbour_info(FakeDataArray(d2, dims=('y', 'x'))))) \
         == S["area_no_roi_no_geocentric"]
+
+
+def test_float32_swath_in_float64_tree_like_the_reference(kd):
+    """kd_tree.py:970-981 transforms float32 lon/lat in float32 (lonlat2xyz on float32 arrays) and only then widens
+    the ECEF coordinates to the float64 tree; the query points are float64.  The index must be built from exactly
+    those coordinates: indices equal to the oracle's on a jittered float32 swath, k = 1 and 8."""
+    from oracle import proj_ref
+    from pyresample_b200 import xarray_nn
+    lon, lat = jittered_swath(300, 200, np.float32, seed=61)
+    area = laea_area(150, 130)
+    tlon, tlat = proj_ref.area_lonlats(area.proj_dict, area.area_extent, area.width, area.height)
+    with np.errstate(invalid="ignore"):
+        vii = (lon >= -180) & (lon <= 180) & (lat <= 90) & (lat >= -90)
+    xyz32 = kd_tree_ref.lonlat2xyz(lon, lat)
+    assert xyz32.dtype == np.float32
+    otree = KDTreeRef(xyz32.reshape(-1, 3)[vii.ravel()].astype(np.float64))
+    voi = np.ones(tlon.shape, dtype=bool)
+    valid, tree = xarray_nn.build_tree(lon, lat)
+    assert np.array_equal(valid, vii)
+    for k in (1, 8):
+        want = kd_tree_ref.query_no_distance(tlon, tlat, voi, valid_input_index=vii, neighbours=k, epsilon=0,
+                                             radius=40000, kdtree=otree)
+        got = kd.query_no_distance(tlon, tlat, voi, neighbours=k, epsilon=0, radius=40000, kdtree=tree)
+        assert np.array_equal(got, want)

@@ -470,13 +470,13 @@ def main():
                                                   neighbours=k)
                 return kd_tree.resample_custom(host_source(), host["data"].numpy(), area, radius, wl.weight_funcs,
                                                neighbours=k)
-            # N > 1: rank 0 uploads, NCCL broadcast, every rank resamples and reads back its own rows
-            if mode == "nearest" and "source_area" not in cfg:
-                # pipelined: coordinates first, the data follow while every rank builds its index and fills its rows
-                return distributed.resample_nearest_from_host(
-                    host["lon"].numpy() if rank == 0 else None, host["lat"].numpy() if rank == 0 else None,
-                    host["data"].numpy() if rank == 0 else None, area, radius, wl.n_src, cfg["lon"].dtype,
-                    cfg["data"].dtype, channels)
+            # N > 1, swath source: source and result live in shared page-locked host memory; every rank uploads its
+            # share of the source over its own PCIe link (all-gather over NVLink) and writes its rows of the result
+            # straight into the one assembled grid
+            if shared is not None:
+                return distributed.resample_nearest_shared(shared["lon"], shared["lat"], shared["data"], shared["out"],
+                                                           area, radius)
+            # otherwise: rank 0 uploads, NCCL broadcast, every rank resamples and reads back its own rows
             for n in names:
                 if rank == 0:
                     dev[n].copy_(host[n], non_blocking=True)
@@ -491,6 +491,13 @@ def main():
                                         _rows=rows)
             return kd_tree._host(blk)
 
+        shared = None
+        if world > 1 and mode == "nearest" and "source_area" not in cfg:
+            shared = {n: distributed.share_host_array(host[n].numpy() if rank == 0 else None,
+                                                      (wl.n_src, channels) if n == "data" else (wl.n_src,), cfg[n].dtype)
+                      for n in names}
+            shared["out"] = distributed.share_host_array(None, (H, W, channels), cfg["data"].dtype)
+            h2d = sum(shared[n].nbytes for n in names)  # over all ranks: each uploads 1 / world of it
         import warnings
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -510,13 +517,23 @@ def main():
                 print("e2e ms per call:", " ".join("%.2f" % v for v in per_call), file=sys.stderr)
         if world > 1:
             e2e_ms = reduce_max(dist, torch, [e2e_ms])[0]
+        if shared is not None:
+            if rank == 0 and os.environ.get("PRS_BENCH_CHECK_SHARED"):
+                want = kd_tree.resample_nearest(geometry.SwathDefinition(host["lon"].numpy(), host["lat"].numpy()),
+                                                host["data"].numpy(), area, radius)
+                assert np.array_equal(shared["out"].array.reshape(want.shape), want, equal_nan=True)
+                print("shared result equals the single-GPU result", file=sys.stderr)
+            dist.barrier()
+            for sh in shared.values():
+                sh.close()
         api = {"nearest": "resample_nearest", "gauss": "resample_gauss", "custom": "resample_custom"}[mode]
         e2e = {"value": n_t_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
                "host_memory": "pinned",
                "api": ("pyresample_b200.kd_tree.%s (numpy in, numpy out)" % api) if world == 1 else
-                      ("pyresample_b200.distributed.resample_nearest_from_host (host arrays on rank 0 in, each rank's "
-                       "rows out to its host)" if mode == "nearest" and "source_area" not in cfg else
+                      ("pyresample_b200.distributed.resample_nearest_shared (source and assembled result in shared "
+                       "page-locked host memory; every rank moves 1/N of each over its own PCIe link)"
+                       if shared is not None else
                        "rank 0 uploads, NCCL broadcast, kd_tree resample of each rank's rows, read-back")}
 
     # ---- C4 as BASELINE.json words it: XArrayResamplerNN next to resample_custom (N = 1 only)

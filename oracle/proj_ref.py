@@ -494,3 +494,228 @@ def area_lonlats(projection, area_extent, width, height, dtype=np.float64, data_
     elif scalar_x and scalar_y:
         lon, lat = lon[0, 0], lat[0, 0]
     return lon, lat
+
+
+# --------------------------------------------------------------------------- forwards
+# PROJ's forward projections (src/projections/{eqc,merc,laea,stere,geos}.cpp, pj_fwd), needed by the bilinear
+# resampler, which projects the source lon/lat into the TARGET CRS (bilinear/_base.py:188-191, 299-307).
+def _modes(d, laea):
+    phi0 = _f(d, "lat_0", 0.0) * DEG_TO_RAD
+    t = abs(phi0)
+    if abs(t - HALFPI) < EPS10:
+        return phi0, ("S" if phi0 < 0 else "N")
+    if laea:
+        return phi0, ("E" if abs(t) < EPS10 else "O")
+    return phi0, ("O" if t > EPS10 else "E")
+
+
+def _fwd_eqc(d, a, es, lam, phi):
+    rc = math.cos(_f(d, "lat_ts", 0.0) * DEG_TO_RAD)
+    return rc * lam, phi - _f(d, "lat_0", 0.0) * DEG_TO_RAD, None
+
+
+def _fwd_merc(d, a, es, lam, phi):
+    k0 = _f(d, "k_0", _f(d, "k", 1.0))
+    if d.get("lat_ts") is not None:
+        phits = abs(_f(d, "lat_ts") * DEG_TO_RAD)
+        k0 = math.cos(phits) / math.sqrt(1 - es * math.sin(phits) ** 2) if es else math.cos(phits)
+    bad = np.abs(np.abs(phi) - HALFPI) <= EPS10
+    with np.errstate(all="ignore"):
+        if es == 0:
+            y = k0 * np.arcsinh(np.tan(phi))
+        else:
+            e = math.sqrt(es)
+            y = k0 * (np.arcsinh(np.tan(phi)) - e * np.arctanh(e * np.sin(phi)))
+    return k0 * lam, y, bad
+
+
+def _fwd_laea(d, a, es, lam, phi):
+    phi0, mode = _modes(d, True)
+    coslam, sinlam = np.cos(lam), np.sin(lam)
+    sinphi = np.sin(phi)
+    bad = np.zeros(lam.shape, dtype=bool)
+    with np.errstate(all="ignore"):
+        if es == 0:
+            cosphi = np.cos(phi)
+            sinb1, cosb1 = math.sin(phi0), math.cos(phi0)
+            if mode in ("E", "O"):
+                y = 1. + cosphi * coslam if mode == "E" else 1. + sinb1 * sinphi + cosb1 * cosphi * coslam
+                bad |= y <= EPS10
+                y = np.sqrt(2. / np.where(bad, 1., y))
+                x = y * cosphi * sinlam
+                y = y * (sinphi if mode == "E" else cosb1 * sinphi - sinb1 * cosphi * coslam)
+            else:
+                if mode == "N":
+                    coslam = -coslam
+                bad |= np.abs(phi + phi0) < EPS10
+                y = math.pi / 4 - phi * .5
+                y = 2. * (np.cos(y) if mode == "S" else np.sin(y))
+                x = y * sinlam
+                y = y * coslam
+            return x, y, bad
+        e = math.sqrt(es)
+        one_es = 1 - es
+        qp = _qsfn(1., e, one_es)
+        rq = math.sqrt(.5 * qp)
+        con = e * sinphi
+        q = one_es * (sinphi / (1 - con * con) - (.5 / e) * np.log((1 - con) / (1 + con)))
+        if mode in ("E", "O"):
+            if mode == "E":
+                dd, sinb1, cosb1 = 1. / rq, 0., 1.
+                xmf, ymf = 1., .5 * qp
+            else:
+                sp0 = math.sin(phi0)
+                sinb1 = _qsfn(sp0, e, one_es) / qp
+                cosb1 = math.sqrt(1. - sinb1 * sinb1)
+                dd = math.cos(phi0) / (math.sqrt(1. - es * sp0 * sp0) * rq * cosb1)
+                xmf, ymf = rq * dd, rq / dd
+            sinb = q / qp
+            cosb2 = 1. - sinb * sinb
+            cosb = np.where(cosb2 > 0, np.sqrt(np.where(cosb2 > 0, cosb2, 0.)), 0.)
+            b = 1. + sinb1 * sinb + cosb1 * cosb * coslam if mode == "O" else 1. + cosb * coslam
+            bad |= np.abs(b) < EPS10
+            b = np.sqrt(2. / np.where(bad, 1., b))
+            if mode == "O":
+                y = ymf * b * (cosb1 * sinb - sinb1 * cosb * coslam)
+            else:
+                y = b * sinb * ymf
+            x = xmf * b * cosb * sinlam
+            return x, y, bad
+        if mode == "N":
+            b = HALFPI + phi
+            q = qp - q
+        else:
+            b = phi - HALFPI
+            q = qp + q
+        bad |= np.abs(b) < EPS10
+        ok = q >= 1e-15
+        bb = np.sqrt(np.where(ok, q, 0.))
+        x = np.where(ok, bb * sinlam, 0.)
+        y = np.where(ok, coslam * (bb if mode == "S" else -bb), 0.)
+        return x, y, bad
+
+
+def _fwd_stere(d, a, es, lam, phi):
+    phi0, mode = _modes(d, False)
+    k0 = _f(d, "k_0", _f(d, "k", 1.0))
+    phits = abs(_f(d, "lat_ts") * DEG_TO_RAD) if d.get("lat_ts") is not None else HALFPI
+    coslam, sinlam = np.cos(lam), np.sin(lam)
+    sinphi = np.sin(phi)
+    bad = np.zeros(lam.shape, dtype=bool)
+    with np.errstate(all="ignore"):
+        if es != 0:
+            e = math.sqrt(es)
+            if mode in ("N", "S"):
+                if abs(phits - HALFPI) < EPS10:
+                    akm1 = 2. * k0 / math.sqrt(math.pow(1 + e, 1 + e) * math.pow(1 - e, 1 - e))
+                else:
+                    t = math.sin(phits)
+                    akm1 = math.cos(phits) / _tsfn(phits, t, e)
+                    t *= e
+                    akm1 /= math.sqrt(1. - t * t)
+                if mode == "S":
+                    phi, coslam, sinphi = -phi, -coslam, -sinphi
+                sp = sinphi * e
+                ts = np.tan(.5 * (HALFPI - phi)) / np.power((1 - sp) / (1 + sp), .5 * e)
+                x = np.where(np.abs(phi - HALFPI) < 1e-15, 0., akm1 * ts)
+                y = -x * coslam
+                return x * sinlam, y, bad
+            t = math.sin(phi0)
+            X1 = 2. * math.atan(math.tan(.5 * (HALFPI + phi0)) * math.pow((1. - t * e) / (1. + t * e), .5 * e)) - HALFPI
+            t *= e
+            akm1 = 2. * k0 * math.cos(phi0) / math.sqrt(1. - t * t)
+            sinX1, cosX1 = math.sin(X1), math.cos(X1)
+            sp = sinphi * e
+            X = 2. * np.arctan(np.tan(.5 * (HALFPI + phi)) * np.power((1. - sp) / (1. + sp), .5 * e)) - HALFPI
+            sinX, cosX = np.sin(X), np.cos(X)
+            if mode == "O":
+                denom = cosX1 * (1. + sinX1 * sinX + cosX1 * cosX * coslam)
+                bad |= denom == 0
+                A = akm1 / np.where(bad, 1., denom)
+                y = A * (cosX1 * sinX - sinX1 * cosX * coslam)
+            else:
+                denom = 1. + cosX * coslam
+                bad |= denom == 0
+                A = akm1 / np.where(bad, 1., denom)
+                y = A * sinX
+            return A * cosX * sinlam, y, bad
+        cosphi = np.cos(phi)
+        if mode in ("O", "E"):
+            sinph0, cosph0 = (math.sin(phi0), math.cos(phi0)) if mode == "O" else (0., 1.)
+            akm1 = 2. * k0
+            y = 1. + cosphi * coslam if mode == "E" else 1. + sinph0 * sinphi + cosph0 * cosphi * coslam
+            bad |= y <= EPS10
+            y = akm1 / np.where(bad, 1., y)
+            x = y * cosphi * sinlam
+            y = y * (sinphi if mode == "E" else cosph0 * sinphi - sinph0 * cosphi * coslam)
+            return x, y, bad
+        akm1 = math.cos(phits) / math.tan(math.pi / 4 - .5 * phits) if abs(phits - HALFPI) >= EPS10 else 2. * k0
+        if mode == "N":
+            coslam, phi = -coslam, -phi
+        bad |= np.abs(phi - HALFPI) < 1e-8
+        y = akm1 * np.tan(math.pi / 4 + .5 * phi)
+        return sinlam * y, y * coslam, bad
+
+
+def _fwd_geos(d, a, es, lam, phi):
+    h = _f(d, "h")
+    flip = str(d.get("sweep", "y")) == "x"
+    rg1 = h / a
+    rg = 1. + rg1
+    with np.errstate(all="ignore"):
+        if es != 0:
+            radius_p, radius_p2, radius_p_inv2 = math.sqrt(1 - es), 1 - es, 1. / (1 - es)
+            phi = np.arctan(radius_p2 * np.tan(phi))
+            r = radius_p / np.hypot(radius_p * np.cos(phi), np.sin(phi))
+        else:
+            radius_p_inv2 = 1.
+            r = 1.
+        Vx = r * np.cos(lam) * np.cos(phi)
+        Vy = r * np.sin(lam) * np.cos(phi)
+        Vz = r * np.sin(phi)
+        bad = ((rg - Vx) * Vx - Vy * Vy - Vz * Vz * radius_p_inv2) < 0.
+        tmp = rg - Vx
+        if flip:
+            x = rg1 * np.arctan(Vy / np.hypot(Vz, tmp))
+            y = rg1 * np.arctan(Vz / tmp)
+        else:
+            x = rg1 * np.arctan(Vy / tmp)
+            y = rg1 * np.arctan(Vz / np.hypot(Vy, tmp))
+    return x, y, bad
+
+
+_FORWARDS = {"eqc": _fwd_eqc, "merc": _fwd_merc, "laea": _fwd_laea, "stere": _fwd_stere, "geos": _fwd_geos}
+
+
+def forward(projection, lon, lat):
+    """(lon, lat) degrees -> projected (x, y) in float64, like ``pyproj.Proj(projection)(lon, lat)``; failures and
+    non-finite input -> inf."""
+    d = parse_proj(projection)
+    name = str(d["proj"])
+    if name == "ups":
+        d = dict(d)
+        d["proj"] = name = "stere"
+        d["lat_0"] = -90.0 if d.get("south") else 90.0
+        d["k_0"], d["x_0"], d["y_0"], d["lon_0"] = 0.994, 2000000.0, 2000000.0, 0.0
+    a, es = ellipsoid(d)
+    lon = np.asarray(lon, dtype=np.float64)
+    lat = np.asarray(lat, dtype=np.float64)
+    pm = _f(d, "pm", 0.0) or 0.0
+    if name in ("longlat", "latlong", "lonlat", "latlon"):
+        return lon - pm, lat * 1.0
+    nonfinite = ~np.isfinite(lon) | ~np.isfinite(lat)
+    lam = (np.where(nonfinite, 0., lon) - pm) * DEG_TO_RAD - _f(d, "lon_0", 0.0) * DEG_TO_RAD
+    phi = np.where(nonfinite, 0., lat) * DEG_TO_RAD
+    over_range = np.abs(phi) - HALFPI > 1e-12  # pj_fwd: latitude outside [-90, 90] is an error
+    if not d.get("over"):
+        lam = _adjlon(lam)
+    x, y, bad = _FORWARDS[name](d, a, es, lam, phi)
+    to_meter = _f(d, "to_meter", None)
+    if to_meter is None:
+        to_meter = _UNITS[str(d.get("units", "m"))]
+    x = (a * x + _f(d, "x_0", 0.0)) / to_meter
+    y = (a * y + _f(d, "y_0", 0.0)) / to_meter
+    fail = nonfinite | over_range
+    if bad is not None:
+        fail = fail | bad
+    return np.where(fail, np.inf, x), np.where(fail, np.inf, y)

@@ -105,7 +105,7 @@ struct WeightedParams {
 // output row is written contiguously.  Per channel the neighbours are accumulated in order i = 0..k-1 like the
 // reference's Python loop; four neighbours are fetched at a time so that their loads are in flight together.
 template <typename Tw, typename Td, typename Ta>
-__global__ void __launch_bounds__(256) gather_weighted_kernel(const WeightedParams P)
+__global__ void __launch_bounds__(256, 2) gather_weighted_kernel(const WeightedParams P)
 {
     const int k = P.k, C = P.channels;
     const int groups = (C + 3) >> 2;
@@ -139,27 +139,23 @@ __global__ void __launch_bounds__(256) gather_weighted_kernel(const WeightedPara
             uint32_t r[4];
             bool missing[4];
             Td v[4][4];
-            Ta w[4][4];
+            Ta w0[4];   // weight of the group's first channel (of all four when they share it)
+            Tw d2[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) r[u] = i0 + u < k ? idx[i0 + u] : 0xFFFFFFFFu;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 missing[u] = r[u] >= P.n_valid;
                 const uint32_t s = missing[u] ? P.first_valid_source : (P.rank_to_source ? __ldg(P.rank_to_source + r[u]) : r[u]);
+                d2[u] = 0;
+                w0[u] = 0;
                 if (i0 + u < k) {
                     load_channels<Td>(data + (size_t)s * C + c0, nc, vec_ok, v[u]);
-                    Tw d2 = 0;
                     if (!P.weights) {
                         const Tw d = missing[u] ? (Tw)1 : dist[i0 + u];
-                        d2 = Ar<Tw>::mul(d, d);
+                        d2[u] = Ar<Tw>::mul(d, d);
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (j > 0 && same_w)
-                            w[u][j] = w[u][0];
-                        else
-                            w[u][j] = P.weights ? (Ta)wplane[j][i0 + u] : (Ta)Ar<Tw>::exp(Ar<Tw>::div(-d2, s2c[j]));
-                    }
+                    w0[u] = P.weights ? (Ta)wplane[0][i0 + u] : (Ta)Ar<Tw>::exp(Ar<Tw>::div(-d2[u], s2c[0]));
                 }
             }
 #pragma unroll
@@ -168,7 +164,10 @@ __global__ void __launch_bounds__(256) gather_weighted_kernel(const WeightedPara
                 if (pass == 0 && !missing[u]) ++count;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const Ta wt = missing[u] ? Ar<Ta>::mul((Ta)0, w[u][j]) : w[u][j];
+                    Ta w = w0[u];
+                    if (j > 0 && !same_w)
+                        w = P.weights ? (Ta)wplane[j][i0 + u] : (Ta)Ar<Tw>::exp(Ar<Tw>::div(-d2[u], s2c[j]));
+                    const Ta wt = missing[u] ? Ar<Ta>::mul((Ta)0, w) : w;
                     if (pass == 0) {
                         res[j] = Ar<Ta>::add(res[j], Ar<Ta>::mul(wt, (Ta)v[u][j]));
                         norm[j] = Ar<Ta>::add(norm[j], wt);

@@ -637,10 +637,10 @@ __device__ __forceinline__ void source_xyz(Tin lo, Tin la, T &x, T &y, T &z)
 // to pass 3.  sparse (a rank of a sharded run keeps a fraction of the points; decided on the host: a coverage mask
 // was given): the coordinates are only loaded for kept points and tmp is only written for them; otherwise all loads
 // are issued up front.
-template <typename Tin, typename T>
+template <typename Tin, typename T, bool sparse>
 __global__ void __launch_bounds__(BUILD_TPB)
     build_xyz_kernel(const Tin *__restrict__ lon, const Tin *__restrict__ lat, int64_t n,
-                     const uint8_t *__restrict__ keep, const IndexMeta *__restrict__ meta, const bool sparse,
+                     const uint8_t *__restrict__ keep, const IndexMeta *__restrict__ meta,
                      Rec<T> *__restrict__ tmp, uint32_t *__restrict__ table)
 {
     // table geometry: one word per thread, one round trip to L2 per block
@@ -716,10 +716,10 @@ __global__ void __launch_bounds__(BUILD_TPB)
 
 // Pass 3: scatter.  table[c + 1] holds start(c) after the exclusive scan and ends as start(c + 1).
 constexpr int SCATTER_ITEMS = 4;
-template <typename T>
+template <typename T, bool sparse>
 __global__ void __launch_bounds__(BUILD_TPB)
     build_scatter_kernel(const Rec<T> *__restrict__ tmp, const uint8_t *__restrict__ keep, int64_t n,
-                         const bool sparse, uint32_t *__restrict__ table, Rec<T> *__restrict__ recs)
+                         uint32_t *__restrict__ table, Rec<T> *__restrict__ recs)
 {
     const int64_t base = (int64_t)blockIdx.x * (BUILD_TPB * SCATTER_ITEMS) + threadIdx.x;
     Rec<T> r[SCATTER_ITEMS];
@@ -763,18 +763,26 @@ __global__ void __launch_bounds__(BUILD_TPB)
 }
 
 // Coarse table: number of points in each COARSE x COARSE block of fine cells, stored as ROW-LOCAL prefix sums
-// (fw + 1 entries per row of coarse cells), so that one warp per row computes counts and prefix sums in one pass
+// (fw + 1 entries per row of coarse cells), so that one block per row computes counts and prefix sums in one pass
 // and no device-wide scan is needed.  Count of the coarse cells [u0, u1] of a row: row[u1 + 1] - row[u0].
-static __global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_start, const IndexMeta *__restrict__ meta,
-                                           uint32_t *__restrict__ ctable)
+constexpr int COARSE_TPB = 256;
+static __global__ void __launch_bounds__(COARSE_TPB)
+    build_coarse_kernel(const uint32_t *__restrict__ cell_start, const IndexMeta *__restrict__ meta,
+                        uint32_t *__restrict__ ctable)
 {
-    const FaceTable &fine = meta->fine, &coarse = meta->coarse;
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
+    __shared__ FaceTable fine, coarse;
+    __shared__ uint32_t warp_tot[COARSE_TPB / 32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x < sizeof(FaceTable) / 4) {
+        reinterpret_cast<uint32_t *>(&fine)[threadIdx.x] = reinterpret_cast<const uint32_t *>(&meta->fine)[threadIdx.x];
+        reinterpret_cast<uint32_t *>(&coarse)[threadIdx.x] = reinterpret_cast<const uint32_t *>(&meta->coarse)[threadIdx.x];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int rows_total = 0;
 #pragma unroll
     for (int f = 0; f < 6; ++f) rows_total += coarse.fh[f];
-    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows_total; r += warps) {
+    for (int r = blockIdx.x; r < rows_total; r += gridDim.x) {
         int face = 0, local = r;
 #pragma unroll
         for (int f = 0; f < 5; ++f)
@@ -785,17 +793,19 @@ static __global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_sta
         const int fw = coarse.fw[face];
         uint32_t *row = ctable + coarse.base[face] + (int64_t)local * (fw + 1);
         const int cv = coarse.fv0[face] + local;
-        uint32_t carry = 0;
-        if (lane == 0) row[0] = 0;
-        for (int i0 = 0; i0 < fw; i0 += 32) {
-            const int i = i0 + lane;
+        if (threadIdx.x == 0) {
+            row[0] = 0;
+            carry_s = 0;
+        }
+        __syncthreads();
+        for (int i0 = 0; i0 < fw; i0 += COARSE_TPB) {
+            const int i = i0 + threadIdx.x;
             uint32_t tot = 0;
             if (i < fw) {
                 const int cu = coarse.fu0[face] + i;
-                for (int q = 0; q < COARSE; ++q) {
-                    const int64_t k0 = table_key(fine, face, cu * COARSE, cv * COARSE + q);
-                    tot += cell_start[k0 + COARSE] - cell_start[k0];
-                }
+                int64_t k0 = table_key(fine, face, cu * COARSE, cv * COARSE);
+#pragma unroll 4
+                for (int q = 0; q < COARSE; ++q, k0 += fine.fw[face]) tot += cell_start[k0 + COARSE] - cell_start[k0];
             }
             uint32_t incl = tot;
 #pragma unroll
@@ -803,8 +813,14 @@ static __global__ void build_coarse_kernel(const uint32_t *__restrict__ cell_sta
                 const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
-            if (i < fw) row[i + 1] = carry + incl;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 31) warp_tot[warp] = incl;
+            __syncthreads();
+            uint32_t before = carry_s;
+            for (int w = 0; w < warp; ++w) before += warp_tot[w];
+            if (i < fw) row[i + 1] = before + incl;
+            __syncthreads();
+            if (threadIdx.x == COARSE_TPB - 1) carry_s = before + incl;
+            __syncthreads();
         }
     }
 }
@@ -904,15 +920,21 @@ int index_build_t(const Tin *lon, const Tin *lat, int64_t n, uint8_t *valid, con
     }
     // pass 2 + scan + pass 3
     const bool sparse = cover != nullptr;  // a rank of a sharded run: most points are skipped
-    build_xyz_kernel<Tin, T><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, ix->meta_dev, sparse, tmp, ix->cell_start);
+    if (sparse)
+        build_xyz_kernel<Tin, T, true><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, ix->meta_dev, tmp, ix->cell_start);
+    else
+        build_xyz_kernel<Tin, T, false><<<(unsigned)n_blocks, BUILD_TPB, 0, st>>>(lon, lat, n, keep, ix->meta_dev, tmp, ix->cell_start);
     PRS_CKL();
     rc = scan_u32_dev(ix->cell_start + 1, ix->cap_cells, &ix->meta_dev->n_cells, 0, st);
     if (rc != PRS_OK) return rc;
     const unsigned scatter_blocks = (unsigned)((n + BUILD_TPB * SCATTER_ITEMS - 1) / (BUILD_TPB * SCATTER_ITEMS));
-    build_scatter_kernel<T><<<scatter_blocks, BUILD_TPB, 0, st>>>(tmp, keep, n, sparse, ix->cell_start, (Rec<T> *)ix->recs);
+    if (sparse)
+        build_scatter_kernel<T, true><<<scatter_blocks, BUILD_TPB, 0, st>>>(tmp, keep, n, ix->cell_start, (Rec<T> *)ix->recs);
+    else
+        build_scatter_kernel<T, false><<<scatter_blocks, BUILD_TPB, 0, st>>>(tmp, keep, n, ix->cell_start, (Rec<T> *)ix->recs);
     PRS_CKL();
     // coarse table (counts + row-local prefix sums in one kernel)
-    build_coarse_kernel<<<n_sm * 4, TPB, 0, st>>>(ix->cell_start, ix->meta_dev, ix->coarse_start);
+    build_coarse_kernel<<<n_sm * 8, COARSE_TPB, 0, st>>>(ix->cell_start, ix->meta_dev, ix->coarse_start);
     PRS_CKL();
     timer.mark("all queued");
     return PRS_OK;

@@ -19,6 +19,16 @@
 
 namespace prs {
 
+// PRS_STATS: event counters for kernel experiments (tools/repro_stats.py reads them through prs_debug_stats)
+#ifdef PRS_STATS
+__device__ unsigned long long g_stats[32];
+#define PRS_STAT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
+#else
+#define PRS_STAT(i, v) \
+    do {               \
+    } while (0)
+#endif
+
 #ifndef PRS_QROWS
 #define PRS_QROWS 8
 #endif
@@ -28,7 +38,7 @@ constexpr int STAGE_ROW_BYTES = 64; // nearest rows up to this size are staged t
 // Resident blocks per SM asked of the compiler for query_kernel (32 * QROWS threads): the search is latency bound,
 // so occupancy beats registers up to k = 8 (64 registers, measured on C2/C3/C5); wider top-k lists get more.
 #ifndef PRS_QUERY_MIN_BLOCKS
-#define PRS_QUERY_MIN_BLOCKS(K) (((K) <= 8 ? 32 : 16) / PRS_QROWS)
+#define PRS_QUERY_MIN_BLOCKS(K) (((K) <= 4 ? 32 : (K) <= 8 ? 24 : 16) / PRS_QROWS)
 #endif
 
 // Records fetched together in the candidate loop of the hot path.
@@ -336,6 +346,7 @@ __device__ __forceinline__ void scan_rect(const IndexView<T> &ix, int face, cons
             // two records in flight per step (one load per iteration leaves the thread waiting a full memory round
             // trip per candidate)
 #pragma unroll 1
+            PRS_STAT(13, e - s);  // candidates offered by the general search
             for (uint32_t i = s; i < e; i += 2) {
                 const Rec<T> r0 = load_rec(ix.recs + i), r1 = load_rec(ix.recs + min(i + 1, e - 1));
                 top.offer(dist2<T>(qx, qy, qz, r0.x, r0.y, r0.z), r0.idx, dub);
@@ -345,6 +356,11 @@ __device__ __forceinline__ void scan_rect(const IndexView<T> &ix, int face, cons
     }
 }
 
+// How phase 0 of the general search grows its block: 0 = rings of two cells walked as four strips, 1 = doubling
+// (2m + 1), 2 = by half (m + m / 2 + 1), the last two scanned as one block with a hole
+#ifndef PRS_GROWTH
+#define PRS_GROWTH 1  // measured on C3 (search + epilogue, ms): strips 5.5, doubling 3.7, by half 3.9
+#endif
 // General search: continues after the home block `hb` around the home cell (cu, cv) has been scanned.
 //   phase 0: grow the block ring by ring until it holds k candidates or covers the radius.  The rings are thin (two
 //            cells): a point OUTSIDE the swath has its k nearest in the sliver where the block first cuts into the
@@ -370,6 +386,9 @@ __device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T 
         return top;
     CellRect rr = bounds_to_cells(hbnd, G);  // everything within the radius on the home face
     int phase = top.full() ? 1 : (clip_rect(ix.fine, hface, rr) ? 0 : 1);
+    PRS_STAT(1, 1);                    // points entering the general search past the coarse test
+    PRS_STAT(2, top.full() ? 1 : 0);   // ... with a full list (only the cap check failed)
+    PRS_STAT(3, top.id[0] == PRS_NONE ? 1 : 0);  // ... with an empty list
     // half-width of what has been visited around (cu, cv)
     int m = hb.u0 <= hb.u1 ? max(max(cu - hb.u0, hb.u1 - cu), max(cv - hb.v0, hb.v1 - cv)) : 0;
     int f = 0;
@@ -403,14 +422,20 @@ __device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T 
                     cc.u0 = far.u0 / COARSE, cc.u1 = far.u1 / COARSE, cc.v0 = far.v0 / COARSE, cc.v1 = far.v1 / COARSE;
                     empty_ahead = coarse_rect_count(ix.coarse, ix.coarse_start, hface, cc) == 0;
                 }
+#if PRS_GROWTH == 0
                 m += empty_ahead ? COARSE : 2;
+#elif PRS_GROWTH == 1
+                m = empty_ahead ? m + COARSE : 2 * m + 1;
+#else
+                m = empty_ahead ? m + COARSE : m + (m >> 1) + 1;
+#endif
                 cnew.u0 = max(cu - m, rr.u0);
                 cnew.u1 = min(cu + m, rr.u1);
                 cnew.v0 = max(cv - m, rr.v0);
                 cnew.v1 = min(cv + m, rr.v1);
                 const bool nonempty = cnew.u0 <= cnew.u1 && cnew.v0 <= cnew.v1;
-                const bool around = nonempty && hb.u0 <= hb.u1 && cnew.u0 <= hb.u0 && cnew.u1 >= hb.u1 &&
-                                    cnew.v0 <= hb.v0 && cnew.v1 >= hb.v1;
+                const bool around = PRS_GROWTH == 0 && nonempty && hb.u0 <= hb.u1 && cnew.u0 <= hb.u0 &&
+                                    cnew.u1 >= hb.u1 && cnew.v0 <= hb.v0 && cnew.v1 >= hb.v1;
                 if (empty_ahead || !nonempty) {
                     sub = 5;  // nothing to scan
                 } else if (around) {
@@ -455,6 +480,11 @@ __device__ __noinline__ TopK<T, K> knn_search_general(const IndexView<T> &ix, T 
                 c = bounds_to_cells(b, G);
                 scan = clip_rect(ix.fine, f, c);
             }
+        }
+        PRS_STAT(4 + phase, 1);  // loop iterations per phase
+        if (scan) {
+            PRS_STAT(7 + phase, 1);  // scans per phase
+            PRS_STAT(10 + phase, (long long)(c.u1 - c.u0 + 1) * (c.v1 - c.v0 + 1));  // cells per phase
         }
         if (scan) scan_rect<T, K>(ix, face, c, skip, hb, qx, qy, qz, dub, top);
         if (phase == 0) {
@@ -534,11 +564,14 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // each row's run with one bulk copy.  The matching stretch of the cell table is staged next to it, so that a thread
 // finds the bounds of its runs without going to global memory.
 constexpr int HULL_ROWS = 64;  // rows of cells a staged tile may span (rows are slotted modulo this)
-constexpr int HOME_MAX = 3;    // largest half-width of a home block: (2 * 3 + 1)^2 cells
+#ifndef PRS_HOME_MAX
+#define PRS_HOME_MAX 4
+#endif
+constexpr int HOME_MAX = PRS_HOME_MAX;  // largest half-width of a home block: (2 * HOME_MAX + 1)^2 cells
 // Shared memory per block: records + cell-table stretch.  A tile's hull holds roughly (points per cell) x (cells the
 // tile covers + a margin of m cells), and cells are sized for ~max(2, k / 2) points.
 #ifndef PRS_STAGE_BYTES
-#define PRS_STAGE_BYTES(K) ((K) <= 4 ? 24576 : 40960)
+#define PRS_STAGE_BYTES(K) ((K) <= 4 ? 24576 : 57344)
 #endif
 constexpr int STAGE_CELLS = 2048;  // entries of the staged cell-table stretch (8 KB)
 struct StageCtx {
@@ -671,7 +704,7 @@ __device__ __forceinline__ Rec<double> lds_rec(const Rec<double> *p)
 // Hot path, records and cell bounds staged in shared memory: the rows of the home block, the point's own row first,
 // then outwards.  Lists of 16 or more are filled chunk-wise through the sorting network (TopK::merge_chunk).
 #ifndef PRS_CHUNK_MIN_K
-#define PRS_CHUNK_MIN_K 16
+#define PRS_CHUNK_MIN_K 16  // for k = 8 the network loses to offer() (C3: 5.6 vs 5.2 ms)
 #endif
 template <typename T, int K>
 __device__ __forceinline__ void scan_home_staged(const StageCtx &sc, const Rec<T> *srecs, const uint32_t *scs,
@@ -679,7 +712,7 @@ __device__ __forceinline__ void scan_home_staged(const StageCtx &sc, const Rec<T
 {
     if (h.hb.u0 > h.hb.u1) return;  // home block outside the table
     const int m = max(h.cv - h.hb.v0, h.hb.v1 - h.cv);
-    if (K >= PRS_CHUNK_MIN_K) {
+    if constexpr (K >= PRS_CHUNK_MIN_K) {
         constexpr int CH = K < 16 ? K : 16;
         // a cursor over the candidates of all rows: row `step` (0: cv; 1: cv - 1; 2: cv + 1; ...), records [i, e)
         int step = -1;
@@ -724,8 +757,7 @@ __device__ __forceinline__ void scan_home_staged(const StageCtx &sc, const Rec<T
             }
             if (__any_sync(__activemask(), any)) top.template merge_chunk<CH>(cd, ci);
         }
-        return;
-    }
+    } else {
 #pragma unroll 1
     for (int step = 0; step <= 2 * m; ++step) {
         // step 0: cv; 1: cv - 1; 2: cv + 1; 3: cv - 2; ...
@@ -741,6 +773,7 @@ __device__ __forceinline__ void scan_home_staged(const StageCtx &sc, const Rec<T
             const Rec<T> r = lds_rec(run + i);
             top.template offer<false>(dist2<T>(qx, qy, qz, r.x, r.y, r.z), r.idx, dub);
         }
+    }
     }
 }
 
@@ -764,6 +797,8 @@ __device__ __forceinline__ void knn_finish(const IndexView<T> &ix, const Home &h
                 return;
         }
     }
+    PRS_STAT(24, 1);                  // points sent to the general search
+    PRS_STAT(25, top.full() ? 1 : 0);  // ... although their list was full
     top = knn_search_general<T, K>(ix, qx, qy, qz, dub, s2r, sr, top, h.hb, h.face, h.cu, h.cv);
 }
 
@@ -1638,7 +1673,10 @@ __global__ void __launch_bounds__(QROWS * 32, PRS_QUERY_MIN_BLOCKS(K))
             mbar_wait(reinterpret_cast<uint64_t *>(&sc.bar), phase);
             phase ^= 1u;
         }
+        if (tid == 0) PRS_STAT(staged ? 14 : 15, 1);  // tiles staged / not staged
         if (valid) {
+            PRS_STAT(0, 1);  // valid points searched
+            PRS_STAT(16 + min(7, max(h.cv - h.hb.v0, h.hb.v1 - h.cv)), 1);  // half-width of the home block
             if (staged) {
                 scan_home_staged<T, K>(sc, srecs, scs, h, qx, qy, qz, dub, top);
             } else {

@@ -11,3 +11,15 @@ namespace prs {
 template int launch_search<PRS_INST_T, PRS_INST_K, PRS_INST_EPI>(const QueryParams &, const IndexRef<PRS_INST_T> &, int64_t,
                                                                  const uint32_t *, const uint32_t *, cudaStream_t);
 }
+
+#if defined(PRS_STATS)
+// one copy of the counters per translation unit: the experiment reads the unit it exercises
+extern "C" int PRS_STATS_NAME(unsigned long long *out)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, prs::g_stats, sizeof(prs::g_stats));
+    unsigned long long zero[32] = {0};
+    cudaMemcpyToSymbol(prs::g_stats, zero, sizeof(zero));
+    return 0;
+}
+#endif

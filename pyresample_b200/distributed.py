@@ -231,3 +231,161 @@ def resample_nearest_from_host(lons, lats, data, target_geo_def, radius_of_influ
 def concat_row_blocks(blocks):
     """Host-side concatenation of contiguous per-rank row blocks."""
     return np.concatenate(blocks, axis=0)
+
+
+# ------------------------------------------------------------------------------------------ shared host memory
+class SharedHostArray(object):
+    """A numpy array in POSIX shared memory that every rank of the node maps and page-locks for CUDA.
+
+    With the source swath and the result grid in such arrays a multi-GPU call needs no host-side funnel: every
+    rank uploads ITS share of the source through its own PCIe link (the shares are exchanged over NVLink) and
+    writes ITS rows of the result straight into the one assembled grid.  ``create=True`` on one rank, then
+    ``SharedHostArray(shape, dtype, name=...)`` on the others (:func:`share_host_array` does both)."""
+
+    def __init__(self, shape, dtype, name=None, create=False):
+        from multiprocessing import shared_memory
+        self.shape, self.dtype = tuple(int(v) for v in shape), np.dtype(dtype)
+        nbytes = max(1, int(np.prod(self.shape)) * self.dtype.itemsize)
+        self._shm = shared_memory.SharedMemory(name=name, create=create, size=nbytes)
+        self.name = self._shm.name
+        self.array = np.ndarray(self.shape, dtype=self.dtype, buffer=self._shm.buf)
+        self._owner = create
+        self._registered = False
+        self.nbytes = nbytes
+
+    def register(self):
+        """Page-lock the mapping for this process' CUDA context (cudaHostRegister): copies to and from the array
+        are then asynchronous and run at full PCIe speed."""
+        if not self._registered:
+            import torch
+            rc = torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, self.nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError("cudaHostRegister failed with error %d" % int(rc))
+            self._registered = True
+        return self
+
+    def tensor(self):
+        import torch
+        return torch.from_numpy(self.array)
+
+    def close(self):
+        if self._registered:
+            import torch
+            torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+            self._registered = False
+        self.array = None
+        self._shm.close()
+        if self._owner:
+            try:
+                self._shm.unlink()
+            except FileNotFoundError:  # pragma: no cover
+                pass
+
+
+def share_host_array(array_or_none, shape, dtype, src=0, group=None):
+    """A :class:`SharedHostArray` holding ``array_or_none`` of rank ``src`` (or uninitialised memory when that is
+    None), attached and registered on every rank."""
+    import torch.distributed as dist
+    rank, world = _world(group)
+    shared = None
+    names = [None]
+    if rank == src:
+        shared = SharedHostArray(shape, dtype, create=True)
+        if array_or_none is not None:
+            shared.array[...] = np.asarray(array_or_none).reshape(shape)
+        names = [shared.name]
+    if world > 1:
+        dist.broadcast_object_list(names, src=src, group=group)
+        if rank != src:
+            shared = SharedHostArray(shape, dtype, name=names[0])
+        dist.barrier(group=group)
+    return shared.register()
+
+
+def _my_chunk(n, world, rank):
+    chunk = -(-n // world)
+    a = min(n, rank * chunk)
+    return chunk, a, min(n, a + chunk)
+
+
+def resample_nearest_shared(lons, lats, data, out, target_geo_def, radius_of_influence, fill_value=0, group=None,
+                            stripe=DEFAULT_STRIPE):
+    """Multi-rank ``resample_nearest`` from and to shared host memory (:class:`SharedHostArray` on every rank).
+
+    ``lons`` / ``lats``: ``(n_source,)`` coordinates, ``data``: ``(n_source, channels)`` rows, ``out``:
+    ``(height, width, channels)`` result grid.  Every rank uploads 1/world of the source through its own PCIe link
+    and the shares are exchanged with an all-gather (NCCL over NVLink); the coordinates go first, so that the index
+    build overlaps the data's upload and exchange; every rank then resamples its stripes of rows and copies them to
+    their place in ``out``.  After the closing barrier the assembled grid is complete in ``out.array`` on every
+    rank.  Same result as ``kd_tree.resample_nearest`` of the whole target."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+    from . import _cabi, kd_tree
+    rank, world = _world(group)
+    target = geometry.as_geo_def(target_geo_def)
+    height, width = target.shape
+    n = int(lons.array.size)
+    channels = int(data.array.shape[1]) if data.array.ndim > 1 else 1
+    rows = shard_rows(height, world, rank) if stripe is None else cyclic_rows(height, world, rank, stripe)
+    chunk, a, b = _my_chunk(n, world, rank)
+    main = torch.cuda.current_stream()
+    up, _ = kd_tree._side_streams()
+    cdt = getattr(torch, lons.dtype.name)
+    ddt = getattr(torch, data.dtype.name)
+    # coordinates: this rank's share of (lon, lat), then everybody's
+    mine = torch.zeros((2, chunk), dtype=cdt, device="cuda")
+    if b > a:
+        mine[0, :b - a].copy_(lons.tensor().reshape(-1)[a:b], non_blocking=True)
+        mine[1, :b - a].copy_(lats.tensor().reshape(-1)[a:b], non_blocking=True)
+    if world > 1:
+        both = torch.empty((world, 2, chunk), dtype=cdt, device="cuda")
+        dist.all_gather_into_tensor(both.view(-1), mine.view(-1), group=group)
+        lon_t = both[:, 0, :].reshape(-1)[:n].contiguous()
+        lat_t = both[:, 1, :].reshape(-1)[:n].contiguous()
+    else:
+        lon_t, lat_t = mine[0, :n], mine[1, :n]
+    # data rows on the side stream, while the index is built from the coordinates
+    up.wait_stream(main)
+    with torch.cuda.stream(up):
+        rows_mine = torch.zeros((chunk, channels), dtype=ddt, device="cuda")
+        if b > a:
+            rows_mine[:b - a].copy_(data.tensor().reshape(n, channels)[a:b], non_blocking=True)
+        if world > 1:
+            rows_all = torch.empty((world * chunk, channels), dtype=ddt, device="cuda")
+            dist.all_gather_into_tensor(rows_all.view(-1), rows_mine.view(-1), group=group)
+        else:
+            rows_all = rows_mine
+        arrived = torch.cuda.Event()
+        arrived.record(up)
+    swath = geometry.SwathDefinition(lon_t, lat_t)
+    source = kd_tree._Source(swath, target, True, radius_of_influence, 1, need_ranks=False,
+                             cover_rows=rows if world > 1 else None)
+    tg, n_t, keep = kd_tree._make_target(source, target, True, radius_of_influence, rows=rows)
+    fill_row = torch.full((channels,), fill_value, dtype=ddt, device="cuda")
+    out_dev = torch.empty((max(n_t, 1), channels), dtype=ddt, device="cuda")
+    main.wait_event(arrived)
+    if n_t > 0:
+        _cabi.check(_cabi.lib().prs_resample_nearest(source.handle, ctypes.byref(tg), float(radius_of_influence),
+                                                    kd_tree._ptr(rows_all), channels * rows_all.element_size(),
+                                                    kd_tree._ptr(fill_row), kd_tree._ptr(out_dev), kd_tree._stream()))
+        # each stripe of rows is one contiguous piece of the assembled grid
+        grid = out.tensor().reshape(height, width * channels)
+        local = out_dev.reshape(-1, width * channels)
+        if world == 1:
+            g_rows = np.arange(height)
+        elif stripe is not None:
+            g_rows = cyclic_global_rows(height, world, rank, stripe)
+        else:
+            g_rows = np.arange(rows[0], rows[0] + rows[1])
+        starts = np.flatnonzero(np.diff(g_rows, prepend=g_rows[0] - 2) != 1)
+        ends = np.append(starts[1:], len(g_rows))
+        for l0, l1 in zip(starts, ends):
+            g0 = int(g_rows[l0])
+            grid[g0:g0 + (l1 - l0)].copy_(local[l0:l1], non_blocking=True)
+    del keep
+    main.synchronize()
+    if world > 1:
+        dist.barrier(group=group)
+    return out.array

@@ -149,6 +149,39 @@ def _resolve_ellipsoid(params):
     return a, 0.0
 
 
+# What each projection reads, beyond the ellipsoid / unit / false-origin parameters common to all.  Anything else in a
+# definition would silently change the coordinates PROJ computes (axis order, datum shifts, a second standard
+# parallel ...): such definitions are refused instead of half-understood.
+_COMMON_KEYS = {"proj", "a", "b", "rf", "f", "es", "e", "R", "ellps", "datum", "units", "to_meter", "x_0", "y_0", "lon_0",
+                "pm", "over", "no_defs", "type", "wktext", "towgs84", "nadgrids", "vunits", "geoidgrids"}
+_PROJ_KEYS = {"longlat": set(), "latlong": set(), "latlon": set(), "lonlat": set(),
+              "eqc": {"lat_ts", "lat_0"}, "merc": {"lat_ts", "k_0", "k", "lat_0"},
+              "laea": {"lat_0"}, "stere": {"lat_0", "lat_ts", "k_0", "k"},
+              "ups": {"south", "lat_0", "lat_ts", "k_0", "k"}, "geos": {"h", "sweep", "lat_0"}}
+_NEUTRAL = {"towgs84": ("0,0,0", "0,0,0,0,0,0,0", "0", 0, 0.0), "nadgrids": ("@null",), "vunits": ("m",)}
+
+
+def _check_known_parameters(p, name):
+    if name not in _PROJ_KEYS:
+        return  # reported as an unsupported projection by the caller
+    for key, value in p.items():
+        if key in _NEUTRAL:
+            if value is True or str(value).replace(" ", "") in [str(v) for v in _NEUTRAL[key]]:
+                continue
+            raise NotImplementedError("+%s=%s changes the coordinates and is not implemented on the device" % (key, value))
+        if key == "geoidgrids":
+            raise NotImplementedError("+geoidgrids is not implemented on the device")
+        if key not in _COMMON_KEYS and key not in _PROJ_KEYS[name]:
+            raise NotImplementedError("+%s is not understood for +proj=%s (supported: %s)"
+                                      % (key, name, ", ".join(sorted(_PROJ_KEYS[name])) or "none"))
+    pm = p.get("pm")
+    if pm is not None:
+        try:
+            float(pm)
+        except (TypeError, ValueError):
+            raise NotImplementedError("named prime meridian +pm=%s (give it in degrees)" % (pm,))
+
+
 def _qsfn(sinphi, e, one_es):
     if e >= 1e-7:
         con = e * sinphi
@@ -163,13 +196,15 @@ class ProjSpec:
         p = proj_to_dict(projection)
         self.params = p
         name = str(p.get("proj"))
+        _check_known_parameters(p, name)
         if name == "ups":
+            # PROJ's ups fixes these whatever the string says (src/projections/stere.cpp, PJ_PROJECTION(ups))
             p = dict(p)
             name = "stere"
             p["lat_0"] = -90.0 if p.get("south") else 90.0
-            p.setdefault("k_0", 0.994)
-            p.setdefault("x_0", 2000000.0)
-            p.setdefault("y_0", 2000000.0)
+            p["k_0"], p["x_0"], p["y_0"], p["lon_0"] = 0.994, 2000000.0, 2000000.0, 0.0
+            p.pop("lat_ts", None)
+            p.pop("k", None)
         self.name = name
         a, es = _resolve_ellipsoid(p)
         s = prs_proj_params()
@@ -192,6 +227,8 @@ class ProjSpec:
         k0 = _num(p, "k_0", _num(p, "k", 1.0))
         if name in _GEOGRAPHIC:
             s.kind = PROJ_LONGLAT
+            if s.lam0 != 0.0:  # PROJ's pj_inv would add it; nothing in the reference's tests or docs uses it
+                raise NotImplementedError("+lon_0 on a geographic CRS is not implemented (use +pm for a shifted meridian)")
         elif name == "eqc":
             s.kind = PROJ_EQC
             rc = math.cos(_num(p, "lat_ts", 0.0) * _D2R)

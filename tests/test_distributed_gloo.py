@@ -85,3 +85,42 @@ def test_shard_rows_uneven():
     from pyresample_b200 import distributed
     assert distributed.shard_plan(10, 4) == [(0, 3), (3, 3), (6, 3), (9, 1)]
     assert distributed.shard_plan(2, 4) == [(0, 1), (1, 1), (2, 0), (2, 0)]
+
+
+def _shared_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pyresample_b200 import distributed
+    # rank 0 owns the array, everybody maps it (register() needs CUDA and is not called here)
+    names = [None]
+    shared = None
+    if rank == 0:
+        shared = distributed.SharedHostArray((6, 5), np.float32, create=True)
+        shared.array[...] = np.arange(30, dtype=np.float32).reshape(6, 5)
+        names = [shared.name]
+    dist.broadcast_object_list(names, src=0)
+    if rank != 0:
+        shared = distributed.SharedHostArray((6, 5), np.float32, name=names[0])
+    dist.barrier()
+    assert shared.array[3, 2] == 17.0
+    # every rank writes the rows it owns under the block-cyclic plan: together they cover the grid exactly once
+    g = distributed.cyclic_global_rows(6, world, rank, stripe=2)
+    shared.array[g] = 100 + rank
+    dist.barrier()
+    full = shared.array.copy()
+    np.save(os.path.join(out_dir, "shared_%d.npy" % rank), full)
+    chunk, a, b = distributed._my_chunk(11, world, rank)
+    assert chunk == 6 and (a, b) == ((0, 6) if rank == 0 else (6, 11))
+    dist.barrier()
+    shared.close()
+    dist.destroy_process_group()
+
+
+def test_shared_host_array_two_ranks(tmp_path):
+    world = 2
+    mp.spawn(_shared_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = np.load(tmp_path / "shared_0.npy"), np.load(tmp_path / "shared_1.npy")
+    assert np.array_equal(a, b)
+    assert np.array_equal(a[:, 0], [100, 100, 101, 101, 100, 100])

@@ -72,3 +72,26 @@ def test_resample_nearest_from_host_single_rank(cuda_lib):
     want = kd_tree.resample_nearest(geometry.SwathDefinition(lon, lat), data, area, 40000, fill_value=-1)
     assert got.shape == want.shape and np.array_equal(got, want)
     assert (want != -1).any()
+
+
+def test_resample_nearest_shared_single_rank(cuda_lib):
+    """Source and result in shared, page-locked host memory (the multi-rank end-to-end path), run on one rank."""
+    from pyresample_b200 import distributed, geometry, kd_tree
+    rng = np.random.default_rng(72)
+    lon = rng.uniform(-30, 30, 70000).astype(np.float32)
+    lat = rng.uniform(-20, 35, 70000).astype(np.float32)
+    data = rng.normal(size=(70000, 3)).astype(np.float32)
+    area = geometry.AreaDefinition("g", "g", "g", "+proj=eqc +datum=WGS84", 800, 450,
+                                   (-10018754.17, -6000000.0, 10018754.17, 7000000.0))
+    s_lon = distributed.share_host_array(lon, lon.shape, lon.dtype)
+    s_lat = distributed.share_host_array(lat, lat.shape, lat.dtype)
+    s_data = distributed.share_host_array(data, data.shape, data.dtype)
+    s_out = distributed.share_host_array(None, area.shape + (3,), data.dtype)
+    try:
+        got = distributed.resample_nearest_shared(s_lon, s_lat, s_data, s_out, area, 40000, fill_value=-1).copy()
+        want = kd_tree.resample_nearest(geometry.SwathDefinition(lon, lat), data, area, 40000, fill_value=-1)
+        assert got.shape == want.shape and np.array_equal(got, want)
+        assert (want != -1).any()
+    finally:
+        for s in (s_lon, s_lat, s_data, s_out):
+            s.close()

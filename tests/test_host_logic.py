@@ -214,3 +214,19 @@ def test_registry_and_small_helpers_without_gpu():
     assert r.version == "0.1" and r._get_src_geo_dims() == ('y', 'x')
     with pytest.raises(ValueError, match="not the same shape"):
         r.precompute(mask=np.zeros((3, 3), dtype=bool))
+
+
+def test_projection_parameters_are_whitelisted():
+    """Definitions the device code would only half understand are refused: unknown keys, named prime
+    meridians, datum shifts, +lon_0 on a geographic CRS; +proj=ups forces PROJ's constants."""
+    from pyresample_b200.proj import ProjSpec
+    for bad in ("+proj=laea +lat_0=50 +lon_0=10 +lat_1=30 +ellps=WGS84", "+proj=stere +lat_0=90 +axis=neu +ellps=WGS84",
+                "+proj=longlat +pm=lisbon +ellps=WGS84", "+proj=merc +towgs84=1,2,3 +ellps=WGS84",
+                "+proj=longlat +lon_0=10 +ellps=WGS84"):
+        with pytest.raises(NotImplementedError):
+            ProjSpec(bad)
+    ProjSpec("+proj=merc +towgs84=0,0,0,0,0,0,0 +ellps=WGS84 +no_defs +type=crs")
+    ups = ProjSpec("+proj=ups +k_0=1 +x_0=5 +y_0=7 +ellps=WGS84").cstruct
+    assert (ups.x0, ups.y0) == (2000000.0, 2000000.0) and ups.phi0 > 1.5
+    ref = ProjSpec("+proj=stere +lat_0=90 +k_0=0.994 +x_0=2000000 +y_0=2000000 +ellps=WGS84").cstruct
+    assert ups.c[0] == ref.c[0]

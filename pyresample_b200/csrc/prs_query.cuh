@@ -1366,6 +1366,59 @@ __device__ __forceinline__ bool tile_cap(const QueryParams &P, uint32_t tile, in
     return true;
 }
 
+// Is any indexed point within `radius` of the cap (unit centre c, squared chord d2m)?  Conservative: true when unsure.
+template <typename T>
+__device__ __forceinline__ bool cap_has_points(const QueryParams &P, const IndexView<T> &ix, float cx, float cy, float cz,
+                                               float d2m)
+{
+    const T dub = (T)(P.radius * P.radius);
+    const float sr = sqrtf(cap_s2<T>(dub));
+    // chord of the union cap on the unit sphere <= tile chord + radius chord (triangle inequality)
+    const float st = (sqrtf(d2m) * 1.0001f + 1e-6f) + sr;
+    const float s2t = st * st;
+    if (!(s2t < 0.25f)) return true;
+    const int hf = home_face(cx, cy, cz);
+    float hb[4];
+    face_bounds(hf, cx, cy, cz, s2t, st, hb);
+    return coarse_count(ix.coarse, ix.coarse_start, ix.Gc, cx, cy, cz, s2t, st, hf, hb, bounds_inside_face(hb)) != 0;
+}
+
+// Per-pixel inverse projections are expensive (ellipsoidal polar stereographic: ~1600 instructions a pixel) and most
+// tiles of a wide grid are nowhere near the swath.  Before transforming all 32 x QROWS points, bound the tile from
+// five of them - its four corner pixels and the centre pixel: the tile is a small rectangle in projected
+// coordinates, the map to the sphere is smooth, so over a tile of at most ~100 km the distance from the centre is
+// largest at a corner up to second-order terms of relative size tile / Earth radius (< 2 %); the cap takes the
+// largest corner distance plus 5 % plus 200 m.  All five valid => every pixel of the tile is valid (the valid
+// region of each projection - plane, disc, rectangle - is convex in projected coordinates).  Returns true when the
+// tile is certainly dead; anything doubtful (an invalid probe, a tile wider than ~120 km on the sphere, extra
+// validity masks) is left to the full evaluation.
+template <typename T>
+__device__ __forceinline__ bool tile_dead_by_probe(const QueryParams &P, const IndexView<T> &ix, int trow0, int tcol,
+                                                   int lane)
+{
+    if (P.valid_extra || ix.n_indexed <= 0) return false;
+    const float invR = (float)(1.0 / PRS_R);
+    const int W = (int)P.grid.width;
+    const int c0 = tcol - lane, c1 = min(c0 + 31, W - 1);
+    const int r0 = trow0, r1 = min(trow0 + QROWS, P.nrows) - 1;
+    bool ok = false;
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (lane < 5) {
+        const int pr = lane == 4 ? (r0 + r1) >> 1 : ((lane & 2) ? r1 : r0);
+        const int pc = lane == 4 ? (c0 + c1) >> 1 : ((lane & 1) ? c1 : c0);
+        T qx, qy, qz;
+        ok = target_point<T, PRS_TK_AREA_GEN>(P, (int64_t)pr * W + pc, pr, pc, qx, qy, qz);
+        ux = (float)qx * invR, uy = (float)qy * invR, uz = (float)qz * invR;
+    }
+    if ((__ballot_sync(0xffffffffu, ok) & 0x1fu) != 0x1fu) return false;
+    const float cx = __shfl_sync(0xffffffffu, ux, 4), cy = __shfl_sync(0xffffffffu, uy, 4), cz = __shfl_sync(0xffffffffu, uz, 4);
+    const float dx = ux - cx, dy = uy - cy, dz = uz - cz;
+    const float d2 = warp_max(lane < 4 ? dx * dx + dy * dy + dz * dz : 0.f);
+    if (d2 > 4e-4f) return false;  // wider than ~127 km: not "small"
+    const float chord = sqrtf(d2) * 1.05f + 3.2e-5f;
+    return !cap_has_points<T>(P, ix, cx, cy, cz, chord * chord);
+}
+
 // tile_live: can any point of the tile have a neighbour?  vmask = this lane's valid points (bit j = tile row j).
 template <typename T, int TK>
 __device__ __forceinline__ bool tile_live(const QueryParams &P, const IndexView<T> &ix, uint32_t tile, int lane,
@@ -1373,23 +1426,14 @@ __device__ __forceinline__ bool tile_live(const QueryParams &P, const IndexView<
 {
     int trow0, tcol;
     tile_origin(P, TK, tile, lane, trow0, tcol);
+    if (TK == PRS_TK_AREA_GEN && tile_dead_by_probe<T>(P, ix, trow0, tcol, lane)) {
+        vmask_out = 0xFFFFFFFFu;  // every pixel of such a tile is valid
+        return false;
+    }
     unsigned vmask;
     float cx, cy, cz, d2m;
     bool is_live = tile_cap<T, TK>(P, tile, trow0, tcol, lane, vmask, cx, cy, cz, d2m) && ix.n_indexed > 0;
-    if (is_live) {
-        const T dub = (T)(P.radius * P.radius);
-        const float sr = sqrtf(cap_s2<T>(dub));
-        // chord of the union cap on the unit sphere <= tile chord + radius chord (triangle inequality)
-        const float st = (sqrtf(d2m) * 1.0001f + 1e-6f) + sr;
-        const float s2t = st * st;
-        if (s2t < 0.25f) {
-            const int hf = home_face(cx, cy, cz);
-            float hb[4];
-            face_bounds(hf, cx, cy, cz, s2t, st, hb);
-            is_live = coarse_count(ix.coarse, ix.coarse_start, ix.Gc, cx, cy, cz, s2t, st, hf, hb,
-                                   bounds_inside_face(hb)) != 0;
-        }
-    }
+    if (is_live) is_live = cap_has_points<T>(P, ix, cx, cy, cz, d2m);
     vmask_out = vmask;
     return is_live;
 }

@@ -485,3 +485,39 @@ def test_source_ends_on_a_horizontal_cube_edge(kd, geometry, dtype):
     tlon = rng.uniform(-1.0, 1.0, 3000)
     tlat = lat_edge + rng.uniform(-0.12, 0.12, 3000)
     _check_against_brute(kd, geometry, lon.ravel(), lat.ravel(), tlon, tlat, 3, 12000.0, dtype)
+
+
+@pytest.mark.parametrize("proj,w,h,ext", [
+    ("+proj=geos +h=35785831 +lon_0=0 +a=6378169 +b=6356583.8", 464, 464, (-5570248.4773, -5567248.0742, 5567248.0742, 5570248.4773)),
+    ("+proj=stere +lat_0=90 +lat_ts=70 +lon_0=-45 +a=6378273 +b=6356889.449", 400, 380, (-3000000., -3000000., 3000000., 3000000.)),
+    ("+proj=laea +lat_0=10 +lon_0=20 +ellps=GRS80", 500, 300, (-2500000., -1500000., 2500000., 1500000.)),
+])
+def test_tiles_culled_from_five_probe_pixels(kd, geometry, proj, w, h, ext):
+    """Areas with a per-pixel inverse projection: tiles are first bounded from their corner and centre pixels only.
+    A narrow band of source points crossing the grid diagonally makes most tiles dead and puts the band's edge
+    through many others - a tile culled by mistake would lose neighbours.  Includes the geos grid whose corners are
+    off the Earth disc (invalid pixels)."""
+    area = geometry.AreaDefinition("a", "a", "a", proj, w, h, ext)
+    olon, olat = area.get_lonlats()
+    fin = np.isfinite(olon)
+    rng = np.random.default_rng(81)
+    # points along the grid's diagonal, +-40 km wide
+    rows = np.linspace(0, h - 1, 30000).astype(int)
+    cols = np.linspace(0, w - 1, 30000).astype(int)
+    ok = fin[rows, cols]
+    lon = olon[rows, cols][ok] + rng.uniform(-0.35, 0.35, ok.sum())
+    lat = np.clip(olat[rows, cols][ok] + rng.uniform(-0.35, 0.35, ok.sum()), -89.9, 89.9)
+    swath = geometry.SwathDefinition(lon, lat)
+    for radius, k in ((4000., 1), (25000., 4)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = kd.get_neighbour_info(swath, area, radius, neighbours=k)
+            want = kd_tree_ref.get_neighbour_info(swath, area, radius, neighbours=k)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        ga, wa = got[2].reshape(len(got[2]), -1), want[2].reshape(len(want[2]), -1)
+        gd, wd = got[3].reshape(ga.shape), want[3].reshape(wa.shape)
+        diff = ga != wa
+        # float64 coordinates differ by a few ulp between CUDA and libm: only exact-tie-scale flips are possible
+        assert not np.any(diff & ~np.isclose(gd, wd, rtol=1e-9, atol=1e-6)), (int(diff.sum()), radius, k)
+        assert np.array_equal(np.isinf(gd), np.isinf(wd))
+        assert 0 < np.isfinite(wd[:, 0]).mean() < 0.5

@@ -242,6 +242,27 @@ int prs_rank_to_source(const uint8_t *valid, int64_t n, uint32_t *out, int64_t *
 int prs_scatter_rows(const uint8_t *mask, int64_t n, int64_t row_bytes, const void *in, const void *fill_row,
                      void *out, void *stream);
 
+/* ---- bilinear resampling on the same index (pyresample/bilinear/_base.py) ------------------------------------
+ * BilinearBase.get_bil_info (:99-119) = a k = 32 prs_query + the two calls below; get_sample_from_bil_info (:251-262)
+ * = prs_bilinear_sample.
+ * prs_project_forward: `pyproj.Proj(target.proj_str)(lon, lat)` (_base.py:188-191, 299-307) for every source point;
+ *   xy_out: double [n * 2] (x, y) pairs, (inf, inf) where the projection fails.
+ * prs_bilinear_info: per target pixel of the area `grid` (n_t = width * height, raveled) the closest neighbour in
+ *   each quadrant among the k neighbours `index` (ranks from prs_query, sentinel n_valid, sorted by distance;
+ *   _base.py:391-411, 573-611) and the fractional distances (_base.py:414-570).
+ *   t_out, s_out: double [n_t] (NaN where no enclosing quadrilateral exists); idx4_out: uint32 [n_t * 4] ranks of the
+ *   upper-left, upper-right, lower-left, lower-right corner (rank of the first neighbour where a quadrant is empty).
+ * prs_bilinear_sample: p1 (1-s)(1-t) + p2 s (1-t) + p3 (1-s) t + p4 s t (_base.py:653-660) in float64 for every
+ *   channel; NaN results become `fill` unless fill is NaN (_numpy_resampler.py:276-282).  out: double [n_out * channels]. */
+int prs_project_forward(const void *lon, const void *lat, int64_t n, int dtype, const prs_proj_params *proj,
+                        void *xy_out, void *stream);
+int prs_bilinear_info(const uint32_t *index, int64_t n_t, int k, uint32_t n_valid, const uint32_t *rank_to_source,
+                      const void *xy, const prs_area_grid *grid, double *t_out, double *s_out, uint32_t *idx4_out,
+                      void *stream);
+int prs_bilinear_sample(const uint32_t *idx4, const double *t, const double *s, int64_t n_out,
+                        const uint32_t *rank_to_source, const void *data, int data_dtype, int channels, double fill,
+                        double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

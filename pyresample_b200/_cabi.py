@@ -17,7 +17,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC_DIR = os.path.join(_HERE, "csrc")
 _SO_PATH = os.environ.get("PRS_B200_LIBRARY") or os.path.join(_HERE, "libprs_b200.so")  # override: kernel experiments
 _SOURCES = ["prs_b200.cu", "prs_query_inst.cu", "prs_classify_inst.cu"]
-_HEADERS = ["prs_common.cuh", "prs_scan.cuh", "prs_proj.cuh", "prs_index.cuh", "prs_query.cuh", "prs_launch.cuh"]
+_HEADERS = ["prs_common.cuh", "prs_scan.cuh", "prs_proj.cuh", "prs_index.cuh", "prs_query.cuh", "prs_launch.cuh",
+            "prs_bilinear.cuh"]
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "prs_b200.h")
 
 PRS_F32, PRS_F64 = 0, 1
@@ -33,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "prs_index_build", "prs_target_coverage", "prs_index_destroy", "prs_index_info", "prs_query", "prs_resample_nearest",
     "prs_resample_scratch_bytes", "prs_resample_nearest_fill", "prs_resample_nearest_search",
     "prs_resample_gauss", "prs_gather_nearest", "prs_gather_weighted", "prs_compact_rows",
-    "prs_rank_to_source", "prs_scatter_rows",
+    "prs_rank_to_source", "prs_scatter_rows", "prs_project_forward", "prs_bilinear_info", "prs_bilinear_sample",
 )
 
 
@@ -172,6 +173,9 @@ def load_library():
         L.prs_compact_rows.argtypes = [vp, i64, i64, vp, vp, pi64, vp]
         L.prs_rank_to_source.argtypes = [vp, i64, vp, pi64, vp]
         L.prs_scatter_rows.argtypes = [vp, i64, i64, vp, vp, vp, vp]
+        L.prs_project_forward.argtypes = [vp, vp, i64, i32, ctypes.POINTER(prs_proj_params), vp, vp]
+        L.prs_bilinear_info.argtypes = [vp, i64, i32, ctypes.c_uint32, vp, vp, ctypes.POINTER(prs_area_grid), vp, vp, vp, vp]
+        L.prs_bilinear_sample.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, dbl, vp, vp]
         for name in EXPORTED_SYMBOLS:
             if name not in ("prs_abi_version", "prs_last_error", "prs_launch_count", "prs_resample_scratch_bytes"):
                 getattr(L, name).restype = i32

@@ -12,6 +12,7 @@
 #include "prs_launch.cuh"
 #include "prs_query.cuh"
 #include "prs_scan.cuh"
+#include "prs_bilinear.cuh"
 
 using namespace prs;
 
@@ -917,6 +918,73 @@ int prs_scatter_rows(const uint8_t *mask, int64_t n, int64_t row_bytes, const vo
     scatter_rows_kernel<<<blocks_for(n), TPB, 0, st>>>(mask, pos, n, row_bytes, vec, in, fill_row, out);
     PRS_CKL();
     PRS_CK(cudaFreeAsync(pos, st));
+    return PRS_OK;
+}
+
+/* ---- bilinear (pyresample/bilinear/_base.py) ------------------------------------------------------------- */
+int prs_project_forward(const void *lon, const void *lat, int64_t n, int dtype, const prs_proj_params *proj, void *xy_out,
+                        void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return PRS_OK;
+    if (!lon || !lat || !proj || !xy_out) return fail(PRS_EINVAL, "null argument");
+    if (dtype == PRS_F32)
+        project_forward_kernel<float><<<blocks_for(n), TPB, 0, st>>>((const float *)lon, (const float *)lat, n, *proj, (double2 *)xy_out);
+    else if (dtype == PRS_F64)
+        project_forward_kernel<double><<<blocks_for(n), TPB, 0, st>>>((const double *)lon, (const double *)lat, n, *proj, (double2 *)xy_out);
+    else
+        return fail(PRS_EINVAL, "dtype must be PRS_F32 or PRS_F64");
+    PRS_CKL();
+    return PRS_OK;
+}
+
+int prs_bilinear_info(const uint32_t *index, int64_t n_t, int k, uint32_t n_valid, const uint32_t *rank_to_source,
+                      const void *xy, const prs_area_grid *grid, double *t_out, double *s_out, uint32_t *idx4_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_t <= 0) return PRS_OK;
+    if (!index || !xy || !grid || !t_out || !s_out || !idx4_out || k < 1) return fail(PRS_EINVAL, "bad argument");
+    if (n_t != grid->width * grid->height) return fail(PRS_EINVAL, "n_t != width * height");
+    BilInfoParams P;
+    P.index = index;
+    P.n_t = n_t;
+    P.k = k;
+    P.n_valid = n_valid;
+    P.rank_to_source = rank_to_source;
+    P.xy = (const double2 *)xy;
+    P.grid = *grid;
+    P.t_out = t_out;
+    P.s_out = s_out;
+    P.idx4_out = idx4_out;
+    bilinear_info_kernel<<<blocks_for(n_t), TPB, 0, st>>>(P);
+    PRS_CKL();
+    return PRS_OK;
+}
+
+int prs_bilinear_sample(const uint32_t *idx4, const double *t, const double *s, int64_t n_out, const uint32_t *rank_to_source,
+                        const void *data, int data_dtype, int channels, double fill, double *out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_out <= 0) return PRS_OK;
+    if (!idx4 || !t || !s || !data || !out || channels < 1) return fail(PRS_EINVAL, "bad argument");
+    BilSampleParams P;
+    P.idx4 = idx4;
+    P.t = t;
+    P.s = s;
+    P.n_out = n_out;
+    P.rank_to_source = rank_to_source;
+    P.data = data;
+    P.channels = channels;
+    P.fill = fill;
+    P.out = out;
+    const unsigned grid = blocks_for(n_out * channels);
+    if (data_dtype == PRS_F32)
+        bilinear_sample_kernel<float><<<grid, TPB, 0, st>>>(P);
+    else if (data_dtype == PRS_F64)
+        bilinear_sample_kernel<double><<<grid, TPB, 0, st>>>(P);
+    else
+        return fail(PRS_EINVAL, "data_dtype must be PRS_F32 or PRS_F64");
+    PRS_CKL();
     return PRS_OK;
 }
 

@@ -144,3 +144,76 @@ def test_xarray_resampler_nn_literals():
     assert np.nansum(nearest_ref.resample(src, area_def, flat2, (0, 1), radius_of_influence=10000)) \
         == S["area_no_roi_no_geocentric"]
     assert np.nansum(nearest_ref.resample(src, area_def, flat3, (0, 1), radius_of_influence=50000)) == S["area_3d"]
+
+
+# ------------------------------------------------------------------------------------------------ bilinear (f2)
+def _bilinear_fixtures():
+    """setUpClass of pyresample/test/test_bilinear.py:42-103."""
+    from pyresample_b200 import geometry
+    target = geometry.AreaDefinition('areaD', 'Europe (3km, HRV, VTC)', 'areaD',
+                                     {'a': '6378144.0', 'b': '6356759.0', 'lat_0': '50.00', 'lat_ts': '50.00',
+                                      'lon_0': '8.00', 'proj': 'stere'}, 4, 4,
+                                     [-1370912.72, -909968.64000000001, 1029087.28, 1490031.3600000001])
+    lons, lats = np.meshgrid(np.linspace(-25., 40., num=100), np.linspace(45., 75., num=100))
+    return target, geometry.SwathDefinition(lons=lons, lats=lats), geometry.SwathDefinition(lons=np.ravel(lons),
+                                                                                          lats=np.ravel(lats))
+
+
+def test_bilinear_fractional_distance_literals():
+    """test_bilinear.py:152-205 (irregular / parallel cases) and :207-219 (division by zero)."""
+    from oracle import bilinear_ref as br
+    irregular = (np.array([[-1., 1.]]), np.array([[1., 2.]]), np.array([[-2., -1.]]), np.array([[2., -4.]]))
+    vert_parallel = (np.array([[-1., 1.]]), np.array([[1., 2.]]), np.array([[-1., -1.]]), np.array([[1., -2.]]))
+    both_parallel = (np.array([[-1., 1.]]), np.array([[1., 1.]]), np.array([[-1., -1.]]), np.array([[1., -1.]]))
+    res = br.distances_irregular(irregular, 0., 0.)
+    assert res[0] == 0.375 and res[1] == 0.5
+    res = br.distances_irregular(vert_parallel, 0., 0.)
+    assert res[0] == 0.5 and np.isnan(res[1])
+    assert tuple(br.distances_uprights_parallel(vert_parallel, 0., 0.)) == (0.5, 0.5)
+    assert tuple(br.distances_parallelogram(both_parallel[:3], 0., 0.)) == (0.5, 0.5)
+    out = np.array([[0.]])
+    for pts, want in ((irregular, (0.375, 0.5)), (both_parallel, (0.5, 0.5)), (vert_parallel, (0.5, 0.5))):
+        t, s = br.fractional_distances(pts, out, out)
+        assert (t, s) == want
+    corner_points = [np.array([[-64.9936752319336, -5.140199184417725]]), np.array([[-64.98487091064453, -5.142156600952148]]),
+                     np.array([[-64.98683166503906, -5.151054859161377]]), np.array([[-64.97802734375, -5.153012275695801]])]
+    t, s = br.fractional_distances(corner_points, np.array([-64.985]), np.array([-5.145]))
+    np.testing.assert_allclose(t, [0.30769689])
+    np.testing.assert_allclose(s, [0.74616628])
+    assert br.solve_quadratic(1, 0, 0) == 0.0 and np.isnan(br.solve_quadratic(1, 2, 1))
+    assert br.solve_quadratic(1, 2, 1, min_val=-2.) == -1.0
+    nan_pts = (np.array([[np.nan, np.nan]]),) + irregular[1:]
+    assert all(np.isnan(v) for v in br.calc_abc(nan_pts, 0.0, 0.0))
+
+
+def test_bilinear_info_and_sampling_literals():
+    """test_bilinear.py:240-383: corners, t / s of pixel 5, NaN pixels, sample sums, masked output."""
+    import warnings
+    from oracle import bilinear_ref as br
+    target, source, source_1d = _bilinear_fixtures()
+    info = br.bil_info(source, target, 50e3, neighbours=32, reduce_data=True)
+    pts = info["corner_points"]
+    assert all(p.shape == (16, 2) for p in pts) and info["index_array"].shape == (16, 4)
+    assert np.sum(~np.isnan(np.sum(pts[0] + pts[1] + pts[2] + pts[3], axis=1))) == 10  # :240-262
+    for reduce_data in (False, True):  # :264-296
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t, s, _, _ = br.get_bil_info(source, target, 50e5, neighbours=32, reduce_data=reduce_data)
+        assert abs(t[5] - 0.730659147133) < 1e-5 and abs(s[5] - 0.310314173004) < 1e-5
+        assert np.isnan(t[12:]).all() and np.isnan(s[12:]).all()
+        assert np.all((t[:12] >= 0) & (t[:12] <= 1) & (s[:12] >= 0) & (s[:12] <= 1))
+    data1 = np.ones((100, 100))
+    t, s, vii, ia = br.get_bil_info(source, target, 50e5, neighbours=32)
+    assert abs(br.get_sample_from_bil_info(data1.ravel(), t, s, vii, ia).ravel()[5] - 1.) < 1e-7  # :298-341
+    assert abs(br.get_sample_from_bil_info(2 * data1.ravel(), t, s, vii, ia).ravel()[5] - 2.) < 1e-7
+    res = br.get_sample_from_bil_info((data1 + 9.5).ravel(), t, s, vii, ia, output_shape=target.shape)
+    assert res.shape == target.shape and np.isnan(res).sum() == 4
+    t1, s1, vii1, ia1 = br.get_bil_info(source_1d, target, 50e5, neighbours=32)  # :343-357
+    res = br.get_sample_from_bil_info((data1 + 9.5).ravel(), t1, s1, vii1, ia1)
+    assert abs(np.nanmin(res) - 10.5) < 1e-7 and abs(np.nanmax(res) - 10.5) < 1e-7 and np.isnan(res).sum() == 4
+    res = br.resample_bilinear(data1, source, target, 50e5, neighbours=32)  # :359-383
+    assert res.shape == target.shape and res.sum() == 12 and (res == 0).sum() == 4
+    res = br.resample_bilinear(data1, source, target, 50e5, neighbours=32, fill_value=None)
+    assert hasattr(res, 'mask') and target.size - res.mask.sum() == 12
+    res = br.resample_bilinear(np.dstack((data1, 2 * data1)), source, target)
+    assert res.shape == target.shape + (2,)

@@ -213,6 +213,22 @@ class AreaDefinition(BaseDefinition):
     def proj_str(self):
         return " ".join("+%s=%s" % (k, v) if v is not True else "+%s" % k for k, v in sorted(self.proj_dict.items()))
 
+    def __getitem__(self, key):
+        """Sub-area of a (row slice, column slice) with unit steps - what a slicer's result is applied with
+        (AreaDefinition.__getitem__, pyresample/geometry.py)."""
+        ys, xs = key
+        r0, r1, rstep = ys.indices(self.height)
+        c0, c1, cstep = xs.indices(self.width)
+        if rstep != 1 or cstep != 1 or r1 <= r0 or c1 <= c0:
+            raise NotImplementedError("only non-empty slices with step 1 select a sub-area")
+        x0, y0, x1, y1 = (float(v) for v in self.area_extent)
+        extent = (x0 + c0 * self.pixel_size_x, y1 - r1 * self.pixel_size_y, x0 + c1 * self.pixel_size_x,
+                  y1 - r0 * self.pixel_size_y)
+        sub = AreaDefinition(self.area_id, self.description, self.proj_id, self.proj_dict, c1 - c0, r1 - r0, extent,
+                             dtype=self.dtype)
+        sub.crop_offset = (self.crop_offset[0] + r0, self.crop_offset[1] + c0)
+        return sub
+
     def get_proj_vectors(self, dtype=None, chunks=None):
         """1-D projection coordinates of the pixel centres (pyresample/geometry.py:1374-1380, 2407-2437).
 

@@ -73,7 +73,7 @@ AREAS = {
     "merc": lambda g: g.AreaDefinition("m", "m", "m", "+proj=merc +lon_0=0 +ellps=WGS84", 260, 240,
                                        (-400000., 4800000., 3500000., 10500000.)),
     "geos": lambda g: g.AreaDefinition("geos", "geos", "geos", "+proj=geos +h=35785831 +lon_0=0 +a=6378169 +b=6356583.8",
-                                       300, 300, (-1500000., 3000000., 2500000., 5400000.)),
+                                       300, 300, (-1500000., 2500000., 2000000., 4500000.)),
 }
 
 

@@ -892,7 +892,9 @@ int index_build_t(const Tin *lon, const Tin *lat, int64_t n, uint8_t *valid, con
     pp.cap_cells = ix->cap_cells;
     // target points per cell: the hot path of the query scans the 3x3 block around a point's cell (9*lambda
     // candidates) and that block should hold the k nearest with room to spare
-    pp.lambda = k_hint > 4 ? 0.5 * (double)k_hint : 2.0;
+    // measured (profiles/r2_experiments.txt): k = 8 is fastest at 6 points per cell (C3 4.84 ms vs 5.17 at 4 and 4.95 at
+    // 8), k = 16 at 8 (C4 53.3 ms vs 54.8 at 12), k = 1 at 2 (C5 6.6 ms vs 7.1 at 3)
+    pp.lambda = k_hint > 8 ? 0.5 * (double)k_hint : (k_hint > 4 ? 0.75 * (double)k_hint : 2.0);
     if (const char *env = getenv("PRS_CELL_OCCUPANCY")) {
         double v = atof(env);
         if (v > 0) pp.lambda = v;

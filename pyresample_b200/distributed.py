@@ -247,6 +247,13 @@ class SharedHostArray(object):
         self.shape, self.dtype = tuple(int(v) for v in shape), np.dtype(dtype)
         nbytes = max(1, int(np.prod(self.shape)) * self.dtype.itemsize)
         self._shm = shared_memory.SharedMemory(name=name, create=create, size=nbytes)
+        if not create:
+            # only the creating rank unlinks the segment: keep this process' resource tracker from trying as well
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:  # pragma: no cover - tracker internals differ between Python versions
+                pass
         self.name = self._shm.name
         self.array = np.ndarray(self.shape, dtype=self.dtype, buffer=self._shm.buf)
         self._owner = create

@@ -230,6 +230,11 @@ int prs_gather_weighted(const uint32_t *index, const void *dist, int64_t n_out, 
                         const double *sigmas_host, double fill,
                         void *out, void *stddev_out, void *count_out, void *stream);
 
+/* What the reference hands to a weight function (kd_tree.py:751-768): the (n_out, k) distances as float64 with 1 in
+ * place of a missing neighbour (index >= n_valid).  n = n_out * k entries; dist_dtype PRS_F32 / PRS_F64. */
+int prs_weight_distances(const uint32_t *index, const void *dist, int dist_dtype, int64_t n, uint32_t n_valid,
+                         double *out, void *stream);
+
 /* ---- helpers ----------------------------------------------------------------------------------------
  * Row compaction by a byte mask (numpy boolean indexing `a[valid]`, kd_tree.py:469-470,530-531):
  * copies the rows with mask != 0, in order; returns the number kept through *n_kept_host (syncs). */

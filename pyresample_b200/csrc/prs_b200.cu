@@ -212,6 +212,15 @@ __global__ void __launch_bounds__(256, 2) gather_weighted_kernel(const WeightedP
     }
 }
 
+// the distances a weight function is given (kd_tree.py:751-768): float64, 1 where the neighbour is missing
+template <typename T>
+__global__ void __launch_bounds__(256) weight_distances_kernel(const uint32_t *__restrict__ index, const T *__restrict__ dist,
+                                                               int64_t n, uint32_t n_valid, double *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __ldcs(index + i) >= n_valid ? 1.0 : (double)__ldcs(dist + i);
+}
+
 __global__ void compact_rows_kernel(const uint8_t *__restrict__ mask, const uint32_t *__restrict__ pos, int64_t n,
                                     int64_t row_bytes, int vec, const void *in, void *out)
 {
@@ -876,6 +885,24 @@ int prs_compact_rows(const uint8_t *mask, int64_t n, int64_t row_bytes, const vo
     }
     PRS_CK(cudaFreeAsync(pos, st));
     PRS_CK(cudaFreeAsync(tot, st));
+    return PRS_OK;
+}
+
+int prs_weight_distances(const uint32_t *index, const void *dist, int dist_dtype, int64_t n, uint32_t n_valid, double *out,
+                         void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return PRS_OK;
+    if (!index || !dist || !out) return fail(PRS_EINVAL, "prs_weight_distances: null array");
+    const int64_t want = (n + 1023) / 1024;  // four entries per thread
+    const int blocks = (int)(want < 148 * 32 ? want : 148 * 32);
+    if (dist_dtype == PRS_F32)
+        weight_distances_kernel<float><<<blocks, 256, 0, st>>>(index, (const float *)dist, n, n_valid, out);
+    else if (dist_dtype == PRS_F64)
+        weight_distances_kernel<double><<<blocks, 256, 0, st>>>(index, (const double *)dist, n, n_valid, out);
+    else
+        return fail(PRS_EINVAL, "prs_weight_distances: distances are float32 or float64");
+    PRS_CKL();
     return PRS_OK;
 }
 

@@ -1049,16 +1049,17 @@ def _eval_weight_planes(weight_funcs, channels, is_multi, dist_np, index_missing
     return np.ascontiguousarray(planes), plane_of_channel
 
 
-_DEVICE_WEIGHT_CHUNK = 1 << 24  # (row, neighbour) entries evaluated per call of a weight function on the device
+_DEVICE_WEIGHT_CHUNK = 1 << 29  # (row, neighbour) entries evaluated per call of a weight function on the device (4 GiB of float64)
 
 
 def _missing_and_dist(idx_t, dist_t, n_valid):
     """Device copies of what the reference feeds to a weight function: the missing-neighbour mask and the distances
     with ``1`` in place of missing neighbours (kd_tree.py:751-768), evaluated in float64."""
     torch = _torch()
-    missing = (idx_t.to(torch.int64) & 0xFFFFFFFF) >= int(n_valid)
-    d = dist_t.to(torch.float64)
-    d[missing] = 1.0
+    idx_t, dist_t = idx_t.contiguous(), dist_t.contiguous()
+    d = torch.empty(dist_t.shape, dtype=torch.float64, device="cuda")
+    _cabi.check(_cabi.lib().prs_weight_distances(_ptr(idx_t), _ptr(dist_t), _tree_code(_np_dtype_of(dist_t)),
+                                                 idx_t.numel(), int(n_valid), _ptr(d), _stream()))
     return d
 
 
@@ -1092,8 +1093,20 @@ def _eval_weight_planes_device(weight_funcs, channels, is_multi, idx_t, dist_t, 
                 wdt = np.asarray(probe).dtype
                 if wdt not in (np.dtype(np.float32), np.dtype(np.float64)):
                     wdt = np.dtype(np.float64)
-            plane = torch.empty((n_out, k), dtype=getattr(torch, wdt.name), device="cuda")
-            flat_i, flat_d, flat_p = idx_t.reshape(-1), dist_t.reshape(-1), plane.reshape(-1)
+            pdt = getattr(torch, wdt.name)
+            flat_i, flat_d = idx_t.reshape(-1), dist_t.reshape(-1)
+            if n_out * k <= _DEVICE_WEIGHT_CHUNK:
+                # one call: a tensor result IS the plane (no copy)
+                w = f(_missing_and_dist(flat_i, flat_d, n_valid))
+                if _is_tensor(w) and w.is_cuda and w.numel() == n_out * k and w.dim() == 1:
+                    plane = w.to(pdt).contiguous().reshape(n_out, k)
+                    seen[id(f)] = len(planes)
+                    planes.append(plane)
+                    dtypes.append(wdt)
+                    plane_of_channel.append(seen[id(f)])
+                    continue
+            plane = torch.empty((n_out, k), dtype=pdt, device="cuda")
+            flat_p = plane.reshape(-1)
             for off in range(0, n_out * k, _DEVICE_WEIGHT_CHUNK):
                 sl = slice(off, min(off + _DEVICE_WEIGHT_CHUNK, n_out * k))
                 d = _missing_and_dist(flat_i[sl], flat_d[sl], n_valid)

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #define PRS_WITH_INDEX_BUILD
@@ -221,21 +222,60 @@ __global__ void __launch_bounds__(256) weight_distances_kernel(const uint32_t *_
         out[i] = __ldcs(index + i) >= n_valid ? 1.0 : (double)__ldcs(dist + i);
 }
 
-__global__ void compact_rows_kernel(const uint8_t *__restrict__ mask, const uint32_t *__restrict__ pos, int64_t n,
-                                    int64_t row_bytes, int vec, const void *in, void *out)
+// Row compaction / scatter: one thread per VEC-byte piece of a row, consecutive threads on consecutive pieces, so a
+// warp reads and writes whole lines whatever the row length (a thread per row touched 32 lines per instruction: the
+// scatter of C4's 128-byte rows ran at 2.1 TB/s).
+template <int VEC> struct Piece;
+template <> struct Piece<16> { typedef uint4 type; };
+template <> struct Piece<8> { typedef uint2 type; };
+template <> struct Piece<4> { typedef uint32_t type; };
+template <> struct Piece<2> { typedef uint16_t type; };
+template <> struct Piece<1> { typedef uint8_t type; };
+
+template <int VEC>
+__global__ void __launch_bounds__(256) compact_rows_kernel(const uint8_t *__restrict__ mask, const uint32_t *__restrict__ pos,
+                                                           int64_t n, int pieces, const void *in, void *out)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !mask[i]) return;
-    copy_row((char *)out + (size_t)pos[i] * row_bytes, (const char *)in + (size_t)i * row_bytes, (int)row_bytes, vec);
+    typedef typename Piece<VEC>::type V;
+    const int64_t total = n * pieces;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / pieces;
+        const int c = (int)(t - row * pieces);
+        if (mask[row]) ((V *)out)[(int64_t)pos[row] * pieces + c] = __ldcs((const V *)in + t);
+    }
 }
 
-__global__ void scatter_rows_kernel(const uint8_t *__restrict__ mask, const uint32_t *__restrict__ pos, int64_t n,
-                                    int64_t row_bytes, int vec, const void *in, const void *fill_row, void *out)
+template <int VEC>
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const uint8_t *__restrict__ mask, const uint32_t *__restrict__ pos,
+                                                           int64_t n, int pieces, const void *in, const void *fill_row,
+                                                           void *out)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const void *src = mask[i] ? (const void *)((const char *)in + (size_t)pos[i] * row_bytes) : fill_row;
-    copy_row((char *)out + (size_t)i * row_bytes, src, (int)row_bytes, vec);
+    typedef typename Piece<VEC>::type V;
+    const int64_t total = n * pieces;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / pieces;
+        const int c = (int)(t - row * pieces);
+        const V v = mask[row] ? __ldcs((const V *)in + (int64_t)pos[row] * pieces + c) : ((const V *)fill_row)[c];
+        __stcs((V *)out + t, v);
+    }
+}
+
+template <typename F> int by_vec(int vec, F &&f)
+{
+    switch (vec) {
+    case 16: return f(std::integral_constant<int, 16>());
+    case 8: return f(std::integral_constant<int, 8>());
+    case 4: return f(std::integral_constant<int, 4>());
+    case 2: return f(std::integral_constant<int, 2>());
+    default: return f(std::integral_constant<int, 1>());
+    }
+}
+
+// grid of a grid-stride kernel over `total` work items: four per thread, at most 32 blocks of 256 threads per SM
+static int stride_blocks(int64_t total)
+{
+    const int64_t want = (total + 1023) / 1024;
+    return (int)(want < 1 ? 1 : (want < 148 * 32 ? want : 148 * 32));
 }
 
 __global__ void rank_to_source_kernel(const uint8_t *__restrict__ valid, const uint32_t *__restrict__ pos, int64_t n,
@@ -873,8 +913,12 @@ int prs_compact_rows(const uint8_t *mask, int64_t n, int64_t row_bytes, const vo
     int rc = scan_u32<uint8_t>(mask, pos, n, 0, tot, st);
     if (rc != PRS_OK) return rc;
     if (in && out) {
-        int vec = pick_vec(row_bytes, in, out, nullptr);
-        compact_rows_kernel<<<blocks_for(n), TPB, 0, st>>>(mask, pos, n, row_bytes, vec, in, out);
+        const int vec = pick_vec(row_bytes, in, out, nullptr);
+        const int pieces = (int)(row_bytes / vec);
+        by_vec(vec, [&](auto v) {
+            compact_rows_kernel<decltype(v)::value><<<stride_blocks(n * pieces), 256, 0, st>>>(mask, pos, n, pieces, in, out);
+            return 0;
+        });
         PRS_CKL();
     }
     if (n_kept_host) {
@@ -941,8 +985,13 @@ int prs_scatter_rows(const uint8_t *mask, int64_t n, int64_t row_bytes, const vo
     PRS_CK(cudaMallocAsync((void **)&pos, sizeof(uint32_t) * (size_t)n, st));
     int rc = scan_u32<uint8_t>(mask, pos, n, 0, nullptr, st);
     if (rc != PRS_OK) return rc;
-    int vec = pick_vec(row_bytes, in, out, fill_row);
-    scatter_rows_kernel<<<blocks_for(n), TPB, 0, st>>>(mask, pos, n, row_bytes, vec, in, fill_row, out);
+    const int vec = pick_vec(row_bytes, in, out, fill_row);
+    const int pieces = (int)(row_bytes / vec);
+    by_vec(vec, [&](auto v) {
+        scatter_rows_kernel<decltype(v)::value><<<stride_blocks(n * pieces), 256, 0, st>>>(mask, pos, n, pieces, in, fill_row,
+                                                                                       out);
+        return 0;
+    });
     PRS_CKL();
     PRS_CK(cudaFreeAsync(pos, st));
     return PRS_OK;

@@ -697,19 +697,22 @@ def _query_device(source, target_geo_def, radius_of_influence, neighbours, reduc
     return idx, dist, valid, bool(flags[0]), int(flags[1])
 
 
-def _compact_rows(mask_t, rows_t):
-    """``rows[mask]`` on the device (prs_compact_rows)."""
+def _compact_rows(mask_t, rows_t, kept=None):
+    """``rows[mask]`` on the device (prs_compact_rows); ``kept`` = the number of set mask bytes when already known."""
     torch = _torch()
     n = mask_t.numel()
     flat = rows_t.reshape(n, -1)
     row_bytes = flat.shape[1] * flat.element_size()
-    kept = ctypes.c_int64(0)
     L = _cabi.lib()
-    _cabi.check(L.prs_compact_rows(_ptr(mask_t), n, row_bytes, None, None, ctypes.byref(kept), _stream()))
-    out = torch.empty((kept.value, flat.shape[1]), dtype=flat.dtype, device="cuda")
-    if kept.value:
+    if kept is None:
+        counted = ctypes.c_int64(0)
+        _cabi.check(L.prs_compact_rows(_ptr(mask_t), n, row_bytes, None, None, ctypes.byref(counted), _stream()))
+        kept = counted.value
+    kept = int(kept)
+    out = torch.empty((kept, flat.shape[1]), dtype=flat.dtype, device="cuda")
+    if kept:
         _cabi.check(L.prs_compact_rows(_ptr(mask_t), n, row_bytes, _ptr(flat), _ptr(out), None, _stream()))
-    return out.reshape((kept.value,) + tuple(rows_t.shape[1:]))
+    return out.reshape((kept,) + tuple(rows_t.shape[1:]))
 
 
 def _create_empty_info(source_geo_def, target_geo_def, neighbours):
@@ -1313,17 +1316,21 @@ def _custom_on_device(source, tgt, radius_of_influence, neighbours, reduce_data,
         # pixels without any neighbour end as fill / NaN / 0 whatever the weights are (norm == 0,
         # kd_tree.py:807-809, 842-858) as long as f(1) - the value the reference feeds for missing
         # neighbours - is finite: only rows with a neighbour are weighted
-        has = (idx[:, 0].to(torch.int64) & 0xFFFFFFFF) < int(source.n_valid)
+        # the nearest neighbour's column: ranks below n_valid, the count itself where there is none (int32 holds both:
+        # a rank is an index into float arrays of at most 2**31 - 1 points)
+        has = idx[:, 0] < int(source.n_valid) if int(source.n_valid) < 2 ** 31 else \
+            (idx[:, 0].to(torch.int64) & 0xFFFFFFFF) < int(source.n_valid)
         if n_invalid:
-            has &= valid.bool()
+            has &= valid.view(torch.bool)
         n_has = int(has.sum())
         if 0 < n_has < n_t // 2:
-            valid = has.to(torch.uint8)
+            valid = has.view(torch.uint8)
             n_invalid = n_t - n_has
+    n_kept = n_t - n_invalid
     if n_invalid:
         voi_t = valid
-        idx = _compact_rows(valid, idx)
-        dist = _compact_rows(valid, dist)
+        idx = _compact_rows(valid, idx, kept=n_kept)
+        dist = _compact_rows(valid, dist, kept=n_kept)
     n_out = idx.shape[0]
     if n_out == 0:
         return None

@@ -629,11 +629,14 @@ template <typename T> __device__ __forceinline__ uint32_t home_density(const Ind
 // Half-width of the home block for k neighbours where a cell holds `lambda` points on average: the k-th neighbour
 // lies ~sqrt(k / (pi lambda)) cells away, and the block must contain the cap of that radius around a point that may
 // sit at the edge of its own cell.
+#ifndef PRS_HOME_FACTOR
+#define PRS_HOME_FACTOR 1.1f
+#endif
 __device__ __forceinline__ int home_halfwidth(int k, float lambda)
 {
     if (!(lambda > 0.f)) return HOME_MAX;
     const float r = sqrtf((float)k / (3.14159265f * lambda));
-    return min(HOME_MAX, max(1, (int)ceilf(1.1f * r)));
+    return min(HOME_MAX, max(1, (int)ceilf(PRS_HOME_FACTOR * r)));
 }
 
 // Bounds [s, e) in recs[] of the three rows of a 3x3 home block, the point's own row first: its candidates are the

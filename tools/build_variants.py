@@ -6,11 +6,11 @@ import sys
 
 sys.path.insert(0, ".")
 VARIANTS = {
-    "v1": "-DPRS_GROWTH=1 -DPRS_CHUNK_MIN_K=16 -DPRS_HOME_MAX=3",
-    "v2": "-DPRS_GROWTH=2 -DPRS_CHUNK_MIN_K=16 -DPRS_HOME_MAX=3",
-    "v3": "-DPRS_GROWTH=1 -DPRS_CHUNK_MIN_K=8 -DPRS_HOME_MAX=3",
-    "v4": "-DPRS_GROWTH=1 -DPRS_CHUNK_MIN_K=16 -DPRS_HOME_MAX=4",
-    "v5": "-DPRS_GROWTH=2 -DPRS_CHUNK_MIN_K=8 -DPRS_HOME_MAX=4",
+    "v1": "-DPRS_HOME_FACTOR=1.3f",
+    "v2": "-DPRS_HOME_FACTOR=1.5f",
+    "v3": "-DPRS_HOME_FACTOR=1.3f -DPRS_HOME_MAX=5",
+    "v4": "-DPRS_HOME_FACTOR=1.5f -DPRS_HOME_MAX=6",
+    "v5": "-DPRS_HOME_FACTOR=1.8f -DPRS_HOME_MAX=6",
 }
 for name, flags in VARIANTS.items():
     env = dict(os.environ, PRS_B200_LIBRARY=os.path.abspath("pyresample_b200/libprs_%s.so" % name), PRS_NVCC_FLAGS=flags,

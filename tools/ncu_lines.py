@@ -10,6 +10,43 @@ import subprocess
 import sys
 
 
+def function_starts(fname):
+    """[(first line, name)] of the device functions defined in pyresample_b200/csrc/<fname> (by their signature lines)."""
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pyresample_b200", "csrc", fname)
+    starts = []
+    try:
+        src = open(path).read().splitlines()
+    except OSError:
+        return starts
+    sig = re.compile(r"^(?:template\s*<[^>]*>\s*)?(?:static\s+)?(?:__device__|__global__|__host__)[^;(]*?\b([A-Za-z_]\w*)\s*\($")
+    for n, line in enumerate(src, 1):
+        if not line or line[0] in " \t/#}":
+            continue
+        head = line.split("(")[0] + "("
+        m = sig.match(head)
+        if m:
+            starts.append((n, m.group(1)))
+        elif n >= 2 and src[n - 2].startswith("template") and re.match(r"^\s+\w+\(", line):
+            pass
+    # a signature split over two lines: `__global__ void __launch_bounds__(..)\n    name(`
+    for n, line in enumerate(src, 1):
+        m = re.match(r"^    ([a-z_]\w*)\(const ", line)
+        if m and n >= 2 and ("__global__" in src[n - 2] or "__device__" in src[n - 2]):
+            starts.append((n - 1, m.group(1)))
+    return sorted(set(starts))
+
+
+def function_of(starts, line):
+    name = "?"
+    for n, f in starts:
+        if n > line:
+            break
+        name = f
+    return name
+
+
 def main():
     rep, kernel = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
@@ -52,6 +89,20 @@ def main():
         for k, v in l[6].items():
             agg[k] = agg.get(k, 0) + v
     print("stall samples:", ", ".join("%s %.1f%%" % (k, 100.0 * v / tot_s) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]))
+    by_fn, cache = {}, {}
+    for l in lines:
+        if l[0] not in cache:
+            cache[l[0]] = function_starts(l[0])
+        key = "%s:%s" % (l[0], function_of(cache[l[0]], l[1])) if cache[l[0]] else l[0]
+        a = by_fn.setdefault(key, [0, 0, 0, 0])
+        a[0] += l[3]
+        a[1] += l[4]
+        a[2] += l[5]
+        a[3] += l[6].get("long_sb", 0)
+    print("\n-- by function (source lines attributed to the function whose definition precedes them)")
+    for key, a in sorted(by_fn.items(), key=lambda kv: -kv[1][2])[:24]:
+        print("%5.1f%% samp %5.1f%% inst  thr %4.1f  long_sb %4.1f%%  %s" % (100.0 * a[2] / tot_s, 100.0 * a[0] / tot_i,
+                                                                         a[1] / max(a[0], 1), 100.0 * a[3] / tot_s, key))
     print("\n-- by warp instructions executed")
     for l in sorted(lines, key=lambda l: -l[3])[:top]:
         print("%5.1f%% inst %5.1f%% samp  thr %4.1f  %s:%d  %s" % (100.0 * l[3] / tot_i, 100.0 * l[5] / tot_s,

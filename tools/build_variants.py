@@ -6,11 +6,10 @@ import sys
 
 sys.path.insert(0, ".")
 VARIANTS = {
-    "v1": "-DPRS_HOME_FACTOR=1.3f",
-    "v2": "-DPRS_HOME_FACTOR=1.5f",
-    "v3": "-DPRS_HOME_FACTOR=1.3f -DPRS_HOME_MAX=5",
-    "v4": "-DPRS_HOME_FACTOR=1.5f -DPRS_HOME_MAX=6",
-    "v5": "-DPRS_HOME_FACTOR=1.8f -DPRS_HOME_MAX=6",
+    "v1": "-DPRS_SEED=0",
+    "v2": "-DPRS_SEED=0 -DPRS_ROW_BATCH=1",
+    "v3": "-DPRS_SEED=1 -DPRS_COOP=1",
+    "v4": "-DPRS_SEED=1 -DPRS_ROW_BATCH=8",
 }
 for name, flags in VARIANTS.items():
     env = dict(os.environ, PRS_B200_LIBRARY=os.path.abspath("pyresample_b200/libprs_%s.so" % name), PRS_NVCC_FLAGS=flags,

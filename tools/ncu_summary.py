@@ -57,8 +57,8 @@ for name, rs in by.items():
         mean("gpu__time_duration.sum", "us"), mean("launch__grid_size"), mean("launch__block_size"),
         mean("launch__registers_per_thread"), mean("launch__shared_mem_per_block_dynamic", "byte")))
     rd, wr = mean("dram__bytes_read.sum", "byte"), mean("dram__bytes_write.sum", "byte")
-    print("  dram read %.1f MB  write %.1f MB  (sum %.1f MB)   dram throughput %.1f %% of peak" % (
-        rd / 1e6, wr / 1e6, (rd + wr) / 1e6, mean("dram__throughput.avg.pct_of_peak_sustained_elapsed")))
+    print("  dram read %.1f MB  write %.1f MB  (sum %.1f MB)   = %.0f GB/s over the kernel's (cold) duration" % (
+        rd / 1e6, wr / 1e6, (rd + wr) / 1e6, (rd + wr) / 1e3 / max(mean("gpu__time_duration.sum", "us"), 1e-9)))
     print("  L2 hit %.1f %%   L1 hit %.1f %%   issue active %.1f %%   achieved occupancy %.1f %%   threads/inst %.1f" % (
         mean("lts__t_sector_hit_rate.pct"), mean("l1tex__t_sector_hit_rate.pct"),
         mean("smsp__issue_active.avg.pct_of_peak_sustained_active"),

@@ -744,18 +744,21 @@ __global__ void __launch_bounds__(BUILD_TPB)
             if (kp[j]) r[j] = load_rec(tmp + base + (int64_t)j * BUILD_TPB);
     }
     // consecutive source points mostly share a cell: one atomic per (warp, cell) instead of one per point
+    // (the atomics of the thread's items are issued before any result is used: their round trips overlap)
     const unsigned lane = threadIdx.x & 31u;
-    uint32_t pos[SCATTER_ITEMS];
+    uint32_t pos[SCATTER_ITEMS], first[SCATTER_ITEMS];
+    unsigned peers[SCATTER_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SCATTER_ITEMS; ++j) peers[j] = __match_any_sync(0xffffffffu, r[j].idx);
 #pragma unroll
     for (int j = 0; j < SCATTER_ITEMS; ++j) {
-        const uint32_t c = r[j].idx;
-        const unsigned peers = __match_any_sync(0xffffffffu, c);
-        const unsigned leader = __ffs(peers) - 1;
-        uint32_t first = 0;
-        if (lane == leader && c != CELL_SKIP) first = atomicAdd(&table[c + 1], (uint32_t)__popc(peers));
-        first = __shfl_sync(0xffffffffu, first, leader);
-        pos[j] = first + __popc(peers & ((1u << lane) - 1u));
+        first[j] = 0;
+        if (lane == (unsigned)(__ffs(peers[j]) - 1) && r[j].idx != CELL_SKIP)
+            first[j] = atomicAdd(&table[r[j].idx + 1], (uint32_t)__popc(peers[j]));
     }
+#pragma unroll
+    for (int j = 0; j < SCATTER_ITEMS; ++j)
+        pos[j] = __shfl_sync(0xffffffffu, first[j], __ffs(peers[j]) - 1) + __popc(peers[j] & ((1u << lane) - 1u));
 #pragma unroll
     for (int j = 0; j < SCATTER_ITEMS; ++j)
         if (r[j].idx != CELL_SKIP)

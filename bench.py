@@ -278,7 +278,8 @@ class Resident(object):
         e0.record()
         source = kd_tree._Source(self.source_dev, self.area, True, self.radius, self.k,
                                  need_ranks=self.mode == "custom",
-                                 cover_rows=self.rows if self.world > 1 else None)
+                                 cover_rows=self.rows if self.world > 1 else None,
+                                 crop_to_cover=self.mode == "nearest" and self.world > 1)
         e1.record()
         channels, data_dev = self.channels, self.data_dev
         if self.mode == "custom":

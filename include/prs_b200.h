@@ -127,6 +127,14 @@ int prs_area_lonlats(const prs_proj_params *proj, const prs_area_grid *grid, int
                      int64_t row0, int64_t row_step, int64_t nrows, int64_t col0, int64_t col_step, int64_t ncols,
                      void *lon_out, void *lat_out, void *xyz_out, void *stream);
 
+/* The same for the WHOLE area as ONE RANK of a row-sharded run sees it: 16 x 16 pixel tiles that cannot hold a pixel
+ * within the coverage mask `cover` (prs_target_coverage of the rank's rows) are not transformed and come out as NaN,
+ * i.e. invalid.  The index built from these arrays with the same `cover` holds exactly the records it would hold
+ * from prs_area_lonlats' output; only the validity mask / the count of valid points differ, so this form is for the
+ * fused nearest path, which consumes neither. */
+int prs_area_lonlats_covered(const prs_proj_params *proj, const prs_area_grid *grid, int dtype, const uint8_t *cover,
+                             void *lon_out, void *lat_out, void *stream);
+
 /* ---- validity masks -------------------------------------------------------------------------------
  * _get_valid_input_index / _get_valid_output_index range test (kd_tree.py:406,454) AND the reduce_data box
  * (data_reduce.py:282-305).  `premask` (optional, 1 = masked out) carries np.ma masks (kd_tree.py:426-428).

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = (
     "prs_resample_scratch_bytes", "prs_resample_nearest_fill", "prs_resample_nearest_search",
     "prs_resample_gauss", "prs_gather_nearest", "prs_gather_weighted", "prs_compact_rows",
     "prs_rank_to_source", "prs_scatter_rows", "prs_project_forward", "prs_bilinear_info", "prs_bilinear_sample",
-    "prs_weight_distances",
+    "prs_weight_distances", "prs_area_lonlats_covered",
 )
 
 
@@ -173,6 +173,8 @@ def load_library():
                                           vp, vp, vp, vp]
         L.prs_compact_rows.argtypes = [vp, i64, i64, vp, vp, pi64, vp]
         L.prs_rank_to_source.argtypes = [vp, i64, vp, pi64, vp]
+        L.prs_area_lonlats_covered.argtypes = [ctypes.POINTER(prs_proj_params), ctypes.POINTER(prs_area_grid), ctypes.c_int, vp, vp,
+                                               vp, vp]
         L.prs_weight_distances.argtypes = [vp, vp, ctypes.c_int, i64, ctypes.c_uint32, vp, vp]
         L.prs_scatter_rows.argtypes = [vp, i64, i64, vp, vp, vp, vp]
         L.prs_project_forward.argtypes = [vp, vp, i64, i32, ctypes.POINTER(prs_proj_params), vp, vp]

@@ -36,7 +36,7 @@ __global__ void lonlat_to_xyz_kernel(const T *__restrict__ lon, const T *__restr
 }
 
 template <typename T>
-__global__ void area_lonlats_kernel(const prs_proj_params P, const prs_area_grid g, int64_t row0, int64_t row_step,
+__global__ void area_lonlats_kernel(const __grid_constant__ prs_proj_params P, const __grid_constant__ prs_area_grid g, int64_t row0, int64_t row_step,
                                     int64_t nrows, int64_t col0, int64_t col_step, int64_t ncols, T *lon_out, T *lat_out,
                                     T *xyz_out)
 {
@@ -54,6 +54,71 @@ __global__ void area_lonlats_kernel(const prs_proj_params P, const prs_area_grid
         xyz_out[3 * i + 1] = y;
         xyz_out[3 * i + 2] = z;
     }
+}
+
+// get_lonlats of a whole area for ONE RANK of a row-sharded run: tiles of 16 x 16 source pixels whose surroundings
+// hold no cell of the rank's coverage mask (prs_target_coverage) are not transformed - their pixels would be dropped
+// by the index build anyway - and come out as NaN (= invalid).  The test is conservative: the tile's four corners and
+// centre must all be valid and lie on one cube face, the bounding box of their coverage cells (~20 km each), grown by
+// one cell, must stay inside the face and span at most 10 cells (a tile under ~160 km: the bulge of its edges beyond
+// the corners' box is far below one cell), and no cell of that box may be set.
+__global__ void __launch_bounds__(128) area_tile_keep_kernel(const __grid_constant__ prs_proj_params P,
+                                                            const __grid_constant__ prs_area_grid g,
+                                                            const uint8_t *__restrict__ cover, int tiles_x, int tiles_y,
+                                                            uint8_t *__restrict__ tile_keep)
+{
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= tiles_x * tiles_y) return;
+    const int64_t W = g.width, H = g.height;
+    const int64_t r0 = (int64_t)(tile / tiles_x) * 16, c0 = (int64_t)(tile % tiles_x) * 16;
+    const int64_t r1 = min(r0 + 15, H - 1), c1 = min(c0 + 15, W - 1);
+    bool keep = false;
+    int face0 = -1, u0 = 0, u1 = 0, v0 = 0, v1 = 0;
+#pragma unroll 1
+    for (int i = 0; i < 5 && !keep; ++i) {
+        const int64_t pr = i == 4 ? (r0 + r1) / 2 : ((i & 2) ? r1 : r0), pc = i == 4 ? (c0 + c1) / 2 : ((i & 1) ? c1 : c0);
+        double lon, lat;
+        area_pixel_lonlat<double>(P, g, pr, pc, lon, lat);
+        if (!(lon >= -180.0 && lon <= 180.0 && lat >= -90.0 && lat <= 90.0)) {
+            keep = true;
+            break;
+        }
+        float slo, clo, sla, cla;
+        __sincosf((float)lon * 0.017453292f, &slo, &clo);
+        __sincosf((float)lat * 0.017453292f, &sla, &cla);
+        int face, iu, iv;
+        face_cell_of(cla * clo, cla * slo, sla, PRS_COVER_CELLS, face, iu, iv);
+        if (i == 0) {
+            face0 = face;
+            u0 = u1 = iu;
+            v0 = v1 = iv;
+        } else {
+            keep = face != face0;
+            u0 = min(u0, iu), u1 = max(u1, iu), v0 = min(v0, iv), v1 = max(v1, iv);
+        }
+    }
+    --u0, ++u1, --v0, ++v1;
+    keep = keep || u0 < 0 || v0 < 0 || u1 >= PRS_COVER_CELLS || v1 >= PRS_COVER_CELLS || u1 - u0 >= 10 || v1 - v0 >= 10;
+    if (!keep) {
+        const uint8_t *c = cover + (size_t)face0 * PRS_COVER_CELLS * PRS_COVER_CELLS;
+        for (int v = v0; v <= v1; ++v)
+            for (int u = u0; u <= u1; ++u) keep = keep || c[(size_t)v * PRS_COVER_CELLS + u] != 0;
+    }
+    tile_keep[tile] = keep ? 1 : 0;
+}
+
+template <typename T>
+__global__ void area_lonlats_masked_kernel(const __grid_constant__ prs_proj_params P, const __grid_constant__ prs_area_grid g,
+                                           const uint8_t *__restrict__ tile_keep, int tiles_x, T *lon_out, T *lat_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t W = g.width;
+    if (i >= W * g.height) return;
+    const int64_t r = i / W, c = i - r * W;
+    T lon = Ar<T>::nan(), lat = Ar<T>::nan();
+    if (tile_keep[(r >> 4) * tiles_x + (c >> 4)]) area_pixel_lonlat<T>(P, g, r, c, lon, lat);
+    lon_out[i] = lon;
+    lat_out[i] = lat;
 }
 
 template <typename T>
@@ -528,6 +593,31 @@ int prs_area_lonlats(const prs_proj_params *proj, const prs_area_grid *grid, int
     else
         return fail(PRS_EINVAL, "dtype must be PRS_F32 or PRS_F64");
     PRS_CKL();
+    return PRS_OK;
+}
+
+int prs_area_lonlats_covered(const prs_proj_params *proj, const prs_area_grid *grid, int dtype, const uint8_t *cover,
+                             void *lon_out, void *lat_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!proj || !grid || !cover || !lon_out || !lat_out) return fail(PRS_EINVAL, "null argument");
+    if (grid->width <= 0 || grid->height <= 0) return PRS_OK;
+    if (dtype != PRS_F32 && dtype != PRS_F64) return fail(PRS_EINVAL, "dtype must be PRS_F32 or PRS_F64");
+    const int64_t tx = (grid->width + 15) / 16, ty = (grid->height + 15) / 16;
+    if (tx * ty > 0x7fffffffLL) return fail(PRS_ENOSUP, "area too large");
+    uint8_t *tile_keep = nullptr;
+    PRS_CK(cudaMallocAsync((void **)&tile_keep, (size_t)(tx * ty), st));
+    area_tile_keep_kernel<<<(unsigned)((tx * ty + 127) / 128), 128, 0, st>>>(*proj, *grid, cover, (int)tx, (int)ty, tile_keep);
+    PRS_CKL();
+    const int64_t n = grid->width * grid->height;
+    if (dtype == PRS_F32)
+        area_lonlats_masked_kernel<float><<<blocks_for(n), TPB, 0, st>>>(*proj, *grid, tile_keep, (int)tx, (float *)lon_out,
+                                                                          (float *)lat_out);
+    else
+        area_lonlats_masked_kernel<double><<<blocks_for(n), TPB, 0, st>>>(*proj, *grid, tile_keep, (int)tx, (double *)lon_out,
+                                                                           (double *)lat_out);
+    PRS_CKL();
+    PRS_CK(cudaFreeAsync(tile_keep, st));
     return PRS_OK;
 }
 

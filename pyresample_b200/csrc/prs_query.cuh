@@ -1833,7 +1833,7 @@ __global__ void coverage_kernel(const __grid_constant__ QueryParams P, uint8_t *
 // Per-row / per-column tables of a separable projection (longlat, eqc, merc): lon depends on the column
 // only and lat on the row only, so the per-pixel transform collapses to two multiplies.
 template <typename T>
-__global__ void area_tables_kernel(const prs_proj_params P, const prs_area_grid g, int64_t row0, int64_t row_block,
+__global__ void area_tables_kernel(const __grid_constant__ prs_proj_params P, const __grid_constant__ prs_area_grid g, int64_t row0, int64_t row_block,
                                    int64_t row_stride, int64_t nrows, ColTab<T> *col_tab, uint8_t *col_ok,
                                    RowTab<T> *row_tab, uint8_t *row_ok)
 {

@@ -360,6 +360,18 @@ def _area_lonlats_device(area, data_slice, dtype, want_xyz=False):
     return lon, lat
 
 
+def _area_lonlats_covered(area, cover):
+    """Raveled lon/lat of a whole area as one rank of a row-sharded run needs them (prs_area_lonlats_covered)."""
+    torch = _torch()
+    td = getattr(torch, np.dtype(area.dtype).name)
+    lon = torch.empty(area.size, dtype=td, device="cuda")
+    lat = torch.empty(area.size, dtype=td, device="cuda")
+    grid = _area_grid(area)
+    _cabi.check(_cabi.lib().prs_area_lonlats_covered(ctypes.byref(area.proj_spec.cstruct), ctypes.byref(grid),
+                                                     _tree_code(area.dtype), _ptr(cover), _ptr(lon), _ptr(lat), _stream()))
+    return lon, lat, None
+
+
 def _area_lonlats_numpy(area, data_slice, dtype):
     lon, lat = _area_lonlats_device(area, data_slice, dtype)
     return lon.cpu().numpy(), lat.cpu().numpy()
@@ -531,15 +543,29 @@ class _Source(object):
     """Device-side state of the source geometry: lon/lat, valid_input_index and the neighbour index."""
 
     def __init__(self, source_geo_def, target_geo_def, reduce_data, radius_of_influence, neighbours,
-                 exclude_mask=None, tree_dtype=None, need_ranks=True, cover_rows=None):
+                 exclude_mask=None, tree_dtype=None, need_ranks=True, cover_rows=None, crop_to_cover=False):
         """``need_ranks``: keep the rank table (index_array is in rank space; the fused resample paths gather by
         source index and do not need it).  ``cover_rows``: this rank's rows of an area target - source points that
-        cannot be within the radius of any of them are left out of the index (multi-GPU row sharding)."""
+        cannot be within the radius of any of them are left out of the index (multi-GPU row sharding).
+        ``crop_to_cover``: an AREA source is not even transformed where the rank cannot need it
+        (prs_area_lonlats_covered): same index, but ``valid`` / ``n_valid`` then describe the cropped source - only
+        for the fused nearest path, which reads neither."""
         _cabi.lib()  # fail loudly when the CUDA library or the GPU is missing: there is no CPU fallback
         source_geo_def = geometry.as_geo_def(source_geo_def)
         target_geo_def = geometry.as_geo_def(target_geo_def)
         self.geo_def = source_geo_def
-        lon_t, lat_t, premask = _geo_lonlats_device(source_geo_def)
+        cover = None
+        lon_t = None
+        if cover_rows is not None and target_geo_def is not None:
+            src_is_area = geometry.is_area(source_geo_def) and getattr(source_geo_def, "lons", None) is None
+            tdt0 = np.dtype(tree_dtype) if tree_dtype is not None else (
+                np.dtype(source_geo_def.dtype) if src_is_area else None)
+            if tdt0 is not None:
+                cover = _target_cover(target_geo_def, cover_rows, radius_of_influence, tdt0)
+            if crop_to_cover and cover is not None and src_is_area and not need_ranks:
+                lon_t, lat_t, premask = _area_lonlats_covered(source_geo_def, cover)
+        if lon_t is None:
+            lon_t, lat_t, premask = _geo_lonlats_device(source_geo_def)
         if lon_t.numel() == 0 or lat_t.numel() == 0:
             raise ValueError('Cannot resample empty data set')
         elif lon_t.numel() != lat_t.numel():
@@ -570,8 +596,7 @@ class _Source(object):
         in_dtype = _np_dtype_of(lon_t)
         handle = ctypes.c_void_p()
         excl = _dev(exclude_mask).reshape(-1) if exclude_mask is not None else None
-        cover = None
-        if cover_rows is not None and target_geo_def is not None:
+        if cover is None and cover_rows is not None and target_geo_def is not None:
             cover = _target_cover(target_geo_def, cover_rows, radius_of_influence, tdt)
         flags = _cabi.PRS_BUILD_COMPUTE_VALID | (_cabi.PRS_BUILD_RANKS if need_ranks else 0)
         _cabi.check(_cabi.lib().prs_index_build(_ptr(lon_t), _ptr(lat_t), lon_t.numel(), _tree_code(in_dtype),
@@ -1194,7 +1219,8 @@ def _resample(source_geo_def, data, target_geo_def, resample_type,
         _gauss_sigma_of(f) is not None for f in (weight_funcs if isinstance(weight_funcs, (list, tuple))
                                                  else [weight_funcs]))
     source = _Source(source_geo_def, target_geo_def, reduce_data, radius_of_influence, neighbours,
-                     need_ranks=not fused, cover_rows=_rows)
+                     need_ranks=not fused, cover_rows=_rows,
+                     crop_to_cover=resample_type == 'nn' and _rows is not None and _is_tensor(data))
     tgt = geometry.as_geo_def(target_geo_def)
     output_shape = tuple(tgt.shape)
     n_src = int(source.lon_t.numel())

@@ -95,3 +95,48 @@ def test_resample_nearest_shared_single_rank(cuda_lib):
     finally:
         for s in (s_lon, s_lat, s_data, s_out):
             s.close()
+
+
+@pytest.mark.parametrize("proj,world,stripe", [("geos", 8, 16), ("geos", 3, 8), ("laea", 4, 8), ("stere", 2, None)])
+def test_area_source_cropped_to_the_ranks_coverage(cuda_lib, proj, world, stripe):
+    """An AREA source of a sharded nearest run is not transformed where the rank cannot need it
+    (prs_area_lonlats_covered): the index holds exactly the records it holds without the crop, the pixels that were
+    transformed carry the same coordinates, and the assembled result equals the unsharded one."""
+    import torch
+
+    from pyresample_b200 import distributed, geometry, kd_tree
+    if proj == "geos":
+        src = geometry.AreaDefinition("fd", "fd", "geos", "+proj=geos +h=35786023 +lon_0=-75 +sweep=x +ellps=GRS80",
+                                      2800, 2800, (-5434894.9, -5434894.9, 5434894.9, 5434894.9))
+        tgt = geometry.AreaDefinition("ll", "ll", "longlat", "+proj=longlat +ellps=GRS80", 1800, 1280,
+                                      (-156.0, -80.0, 6.0, 80.0))
+        radius = 8000.0
+    elif proj == "laea":
+        src = laea_area(2400, 2300, half=3000000.0, lat_0=50, lon_0=10)
+        tgt = geometry.AreaDefinition("w", "w", "eqc", "+proj=eqc +datum=WGS84", 720, 361,
+                                      (-20037508.342789244, -10018754.171394622, 20037508.342789244, 10018754.171394622))
+        radius = 30000.0
+    else:
+        src = geometry.AreaDefinition("ps", "ps", "stere", "+proj=stere +lat_0=90 +lat_ts=70 +lon_0=-45 +ellps=WGS84",
+                                      2400, 2400, (-3000000.0, -3000000.0, 3000000.0, 3000000.0))
+        tgt = laea_area(1000, 800, half=2500000.0, lat_0=75, lon_0=-30)
+        radius = 12000.0
+    data = torch.from_numpy(np.random.default_rng(7).standard_normal(src.size).astype(np.float32)).cuda()
+    full = kd_tree.resample_nearest(src, data, tgt, radius, fill_value=-1).cpu().numpy()
+    assert (full != -1).mean() > 0.05
+    lon_full, lat_full, _ = kd_tree._geo_lonlats_device(src)
+    blocks, dropped = [], 0
+    for rank in range(world):
+        rows = distributed.shard_rows(tgt.shape[0], world, rank) if stripe is None else \
+            distributed.cyclic_rows(tgt.shape[0], world, rank, stripe)
+        plain = kd_tree._Source(src, tgt, True, radius, 1, need_ranks=False, cover_rows=rows)
+        crop = kd_tree._Source(src, tgt, True, radius, 1, need_ranks=False, cover_rows=rows, crop_to_cover=True)
+        assert crop.index.n_indexed == plain.index.n_indexed
+        there = ~torch.isnan(crop.lon_t)
+        assert torch.equal(crop.lon_t[there], lon_full[there]) and torch.equal(crop.lat_t[there], lat_full[there])
+        dropped += int((~there & ~torch.isnan(lon_full) & (lon_full.abs() <= 180)).sum())
+        blocks.append(kd_tree._resample(src, data, tgt, 'nn', radius, neighbours=1, fill_value=-1, _rows=rows).cpu().numpy())
+    got = distributed.assemble_rows(blocks, tgt.shape[0], stripe)
+    assert np.array_equal(got, full)
+    n_valid = int((~torch.isnan(lon_full) & (lon_full.abs() <= 180)).sum())
+    assert dropped > 0.05 * (world - 1) * n_valid  # the crop really skips part of the source (how much: stripe spacing)

@@ -219,3 +219,45 @@ def test_float32_swath_in_float64_tree_like_the_reference(kd):
                                              radius=40000, kdtree=otree)
         got = kd.query_no_distance(tlon, tlat, voi, neighbours=k, epsilon=0, radius=40000, kdtree=tree)
         assert np.array_equal(got, want)
+
+
+def test_xarray_resampler_nn_computes_nothing_until_asked(kd):
+    """test_kd_tree.py:908-919 (`assert_maximum_dask_computes(0)` around get_neighbour_info and
+    get_sample_from_neighbour_info): nothing is computed until a result is used.  Counted with the module's own
+    counter of deferred computations that ran (dask is not installed here: the results are LazyArrays)."""
+    import reference_cases as rc
+    from pyresample_b200 import _cabi, geometry, xarray_nn
+    area_def, src, d2, _ = rc.xarray_nn_fixtures(geometry)
+    L = _cabi.lib()
+    ran0, launches0 = xarray_nn.COMPUTE_COUNT, L.prs_launch_count()
+    resampler = kd.XArrayResamplerNN(src, area_def, radius_of_influence=50000, neighbours=1)
+    ninfo = resampler.get_neighbour_info()
+    assert ninfo[3] is None
+    for val in ninfo[:3]:
+        assert hasattr(val, "compute")  # lazy (dask array or LazyArray)
+    res = resampler.get_sample_from_neighbour_info(FakeDataArray(d2, dims=('y', 'x')))
+    assert hasattr(res.data, "compute")
+    assert xarray_nn.COMPUTE_COUNT == ran0  # no deferred computation (index build, search, gather) has run yet
+    total = np.nansum(_values(res))
+    assert total == rc.XARRAY_NN_SUMS["area_to_area"]
+    assert xarray_nn.COMPUTE_COUNT > ran0 and L.prs_launch_count() > launches0
+    # a second use does not compute the tree / the query again
+    ran1 = xarray_nn.COMPUTE_COUNT
+    ia = _values(ninfo[2])
+    assert ia.shape == (800, 800, 1) and ia.dtype == np.int64
+    assert xarray_nn.COMPUTE_COUNT <= ran1 + 1
+
+
+def test_query_resample_kdtree_matches_get_neighbour_info(kd):
+    """kd_tree.py:983-1004: the class's own query step on a tree from _create_resample_kdtree."""
+    import reference_cases as rc
+    from pyresample_b200 import geometry
+    area_def, src, _, _ = rc.xarray_nn_fixtures(geometry)
+    resampler = kd.XArrayResamplerNN(src, area_def, radius_of_influence=50000, neighbours=1)
+    vii, voi, ia, _ = resampler.get_neighbour_info()
+    valid_input_index, tree = resampler._create_resample_kdtree()
+    assert np.array_equal(_values(valid_input_index), _values(vii))
+    tlons, tlats = area_def.get_lonlats()
+    res, dist = resampler.query_resample_kdtree(tree, tlons, tlats, np.ones(tlons.shape, dtype=bool), None)
+    assert dist is None  # the reference returns (index_array, None) as well
+    assert np.array_equal(_values(res), _values(ia))

@@ -569,7 +569,7 @@ constexpr int HULL_ROWS = 64;  // rows of cells a staged tile may span (rows are
 #endif
 constexpr int HOME_MAX = PRS_HOME_MAX;  // largest half-width of a home block: (2 * HOME_MAX + 1)^2 cells
 // Shared memory per block: records + cell-table stretch.  A tile's hull holds roughly (points per cell) x (cells the
-// tile covers + a margin of m cells), and cells are sized for ~max(2, k / 2) points.
+// tile covers + a margin of m cells), and cells are sized for 2 .. k / 2 points (index_build_t: 2 for k <= 4, 0.75 k up to 8, 0.5 k above).
 #ifndef PRS_STAGE_BYTES
 #define PRS_STAGE_BYTES(K) ((K) <= 4 ? 24576 : 57344)
 #endif
